@@ -1,0 +1,154 @@
+"""TEST INFRASTRUCTURE -- ctypes binding of oracle/_ref/libpt_ref_host.so.
+
+That library is the reference's OWN tracing code (cuSrc/{object,material,bvh,motional_camera}.cu
+under /root/reference) compiled unmodified for the host by oracle/ref_build/Makefile, plus a
+harness restating SamplePixel/Miss (cuSrc/path_tracer.cu:117-175).  Only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` legs may import this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libpt_ref_host.so")
+
+
+class RefMaterial(C.Structure):
+    _fields_ = [
+        ("type", C.c_int32),
+        ("have_tex", C.c_int32),
+        ("kd", C.c_float * 3),
+        ("refractive_index", C.c_float),
+        ("emit_intensity", C.c_float),
+        ("smoothness", C.c_float),
+        ("reflectivity", C.c_float),
+    ]
+
+
+class RefStats(C.Structure):
+    _fields_ = [("paths", C.c_ulonglong), ("segments", C.c_ulonglong), ("misses", C.c_ulonglong),
+                ("depth_exhausted", C.c_ulonglong)]
+
+
+def available() -> bool:
+    return os.path.exists(LIB_PATH)
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+class RefHost:
+    """One process-wide scene (the reference keeps its BVH in file-static state, bvh.cu:16-20)."""
+
+    def __init__(self, path: str = LIB_PATH):
+        self.lib = C.CDLL(path)
+        L = self.lib
+        L.ref_add_object.restype = C.c_int
+        L.ref_add_object.argtypes = [C.c_int, C.POINTER(C.c_float), C.c_float, C.c_float, C.c_float,
+                                     C.POINTER(RefMaterial)]
+        L.ref_build.restype = C.c_int
+        L.ref_sizeof.restype = C.c_int
+        L.ref_max_threads.restype = C.c_int
+        self.n_prims = 0
+
+    # -- scene ---------------------------------------------------------------------------------
+    @staticmethod
+    def _mat(m) -> RefMaterial:
+        r = RefMaterial()
+        r.type = int(m["type"]); r.have_tex = 0
+        r.kd[0], r.kd[1], r.kd[2] = [float(v) for v in m["kd"]]
+        r.refractive_index = float(m["refractive_index"]); r.emit_intensity = float(m["emit_intensity"])
+        r.smoothness = float(m["smoothness"]); r.reflectivity = float(m["reflectivity"])
+        return r
+
+    def load_scene(self, scene) -> int:
+        self.lib.ref_reset()
+        mats = [self._mat(m) for m in scene.materials]
+        for i in range(scene.n_prims):
+            c = (C.c_float * 3)(*[float(v) for v in scene.center[i]])
+            self.lib.ref_add_object(int(scene.prim_type[i]), c, float(scene.radius[i]), float(scene.y_pos[i]),
+                                    float(scene.height[i]), C.byref(mats[int(scene.mat_idx[i])]))
+        self.n_prims = scene.n_prims
+        n_nodes = self.lib.ref_build()
+        self.set_camera(scene.camera)
+        return n_nodes
+
+    def leaf_order(self) -> np.ndarray:
+        out = np.full(self.n_prims, -1, np.int32)
+        self.lib.ref_leaf_order(_p(out, C.c_int32))
+        return out
+
+    def set_sky(self, rgba: np.ndarray, quarter_rows: bool = True):
+        rgba = np.ascontiguousarray(rgba, np.uint8)
+        h, w = rgba.shape[:2]
+        self.lib.ref_set_sky(_p(rgba, C.c_uint8), C.c_int(w), C.c_int(h), C.c_int(1 if quarter_rows else 0))
+
+    def set_camera(self, cam) -> np.ndarray:
+        out = np.zeros(19, np.float32)
+        o = (C.c_float * 3)(*[float(v) for v in cam.origin])
+        a = (C.c_float * 3)(*[float(v) for v in cam.look_at])
+        self.lib.ref_camera_setup(C.c_int(cam.width), C.c_int(cam.height), o, a, C.c_float(cam.view_fov),
+                                  C.c_float(cam.lens_radius), _p(out, C.c_float))
+        return out
+
+    def camera_op(self, pose7: np.ndarray, op: int, arg: float) -> np.ndarray:
+        p = np.ascontiguousarray(pose7, np.float32).copy()
+        self.lib.ref_camera_op(_p(p, C.c_float), C.c_int(op), C.c_float(arg))
+        return p
+
+    # -- level-1 / level-2 entry points ------------------------------------------------------------
+    def trace(self, rays8: np.ndarray):
+        rays8 = np.ascontiguousarray(rays8, np.float32)
+        n = rays8.shape[0]
+        prim = np.empty(n, np.int32); t = np.empty(n, np.float32)
+        nrm = np.empty((n, 3), np.float32); pos = np.empty((n, 3), np.float32)
+        self.lib.ref_trace(C.c_int(n), _p(rays8, C.c_float), _p(prim, C.c_int32), _p(t, C.c_float),
+                           _p(nrm, C.c_float), _p(pos, C.c_float))
+        return prim, t, nrm, pos
+
+    def shade(self, materials: np.ndarray, mat_idx, pos, nrm, in_dir, u3):
+        n = len(mat_idx)
+        mats = (RefMaterial * len(materials))(*[self._mat(m) for m in materials])
+        mat_idx = np.ascontiguousarray(mat_idx, np.int32)
+        pos, nrm, in_dir, u3 = [np.ascontiguousarray(a, np.float32) for a in (pos, nrm, in_dir, u3)]
+        b = np.empty((n, 3), np.float32); a = np.empty((n, 3), np.float32); r = np.empty((n, 3), np.float32)
+        nd = np.empty(n, np.int32)
+        self.lib.ref_shade(C.c_int(n), mats, _p(mat_idx, C.c_int32), _p(pos, C.c_float), _p(nrm, C.c_float),
+                           _p(in_dir, C.c_float), _p(u3, C.c_float), _p(b, C.c_float), _p(a, C.c_float),
+                           _p(r, C.c_float), _p(nd, C.c_int32))
+        return b, a, r, nd
+
+    def raygen(self, xy, u3):
+        xy = np.ascontiguousarray(xy, np.int32); u3 = np.ascontiguousarray(u3, np.float32)
+        n = xy.shape[0]
+        rays = np.empty((n, 8), np.float32)
+        self.lib.ref_raygen(C.c_int(n), _p(xy, C.c_int32), _p(u3, C.c_float), _p(rays, C.c_float))
+        return rays
+
+    def sky_lookup(self, dirs):
+        dirs = np.ascontiguousarray(dirs, np.float32)
+        out = np.empty_like(dirs)
+        self.lib.ref_sky_lookup(C.c_int(dirs.shape[0]), _p(dirs, C.c_float), _p(out, C.c_float))
+        return out
+
+    # -- full render -------------------------------------------------------------------------------
+    def render(self, cam, spp: int, max_depth: int = 8, seed: int = 0, first_sample: int = 0, nthreads: int = 0,
+               want_normals: bool = False):
+        """Returns (sum_rgb [H,W,3] float32 -- per-pixel SUM over the samples, stats dict[, normals])."""
+        self.set_camera(cam)
+        out = np.zeros((cam.height, cam.width, 3), np.float32)
+        nrm = np.zeros((cam.height, cam.width, 3), np.float32) if want_normals else None
+        st = RefStats()
+        self.lib.ref_render(C.c_int(spp), C.c_int(first_sample), C.c_int(max_depth), C.c_ulonglong(seed),
+                            C.c_int(nthreads), _p(out, C.c_float),
+                            _p(nrm, C.c_float) if want_normals else None, C.byref(st))
+        stats = {"paths": st.paths, "segments": st.segments, "misses": st.misses,
+                 "depth_exhausted": st.depth_exhausted}
+        return (out, stats, nrm) if want_normals else (out, stats)
+
+    def max_threads(self) -> int:
+        return int(self.lib.ref_max_threads())
