@@ -1,0 +1,877 @@
+// pt_api.cu -- host side of libpt_b200.so: scene container, LBVH build driver, wave scheduler and the
+// extern "C" entry points declared in include/pt_api.h.  There is no CPU fallback anywhere in this file:
+// without a CUDA device pt_scene_create fails with PT_ERR_NO_DEVICE.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/pt_api.h"
+#include "pt_lbvh.cuh"
+#include "pt_math.cuh"
+#include "pt_wavefront.cuh"
+
+using namespace pt;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(PT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" + \
+                                         std::to_string(__LINE__) + ")");                                \
+    } while (0)
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t reserve(size_t count) {
+        if (count <= n) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+struct HostPrim {
+    int type;
+    float c[3];
+    float radius, y_pos, height;
+    int mat_slot;
+};
+
+struct MatKey {
+    pt_material m;
+    bool operator<(const MatKey& o) const { return memcmp(&m, &o.m, sizeof(pt_material)) < 0; }
+};
+
+struct Texture { cudaArray_t arr = nullptr; cudaTextureObject_t obj = 0; };
+
+}  // namespace
+
+struct pt_scene {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    // host description
+    std::vector<HostPrim> prims;
+    std::vector<pt_material> materials;      // distinct materials, slot order
+    std::map<MatKey, int> material_slots;
+    bool dirty = true, built = false;
+    // options
+    uint32_t opt_wave_paths = 16u << 20;
+    int opt_stage_timing = 0;
+    int opt_tie_order = 1;
+    int opt_sky_quarter = 1;
+    // device scene
+    DevBuf<float4> geo0, geo1, nodes, leaf_mn, leaf_mx, inner_mn, inner_mx;
+    DevBuf<MaterialRec> mats;
+    DevBuf<float> plat_y;
+    DevBuf<int> plat_id, bvh_prims, parent_inner, parent_leaf, flags;
+    DevBuf<int2> children;
+    DevBuf<uint32_t> codes, codes_sorted, ids, ids_sorted, bounds6, tie_rank;
+    DevBuf<unsigned char> cub_tmp;
+    int n_plat = 0, n_tree = 0, has_emitters = 0;
+    Texture sky;
+    std::map<uint64_t, Texture> textures;
+    // frame state
+    int width = 0, height = 0;
+    DevBuf<float4> accum;
+    // wave queues
+    DevBuf<float4> q_o[2], q_d[2], q_thr[2], path_out;
+    DevBuf<uint2> hit;
+    DevBuf<uint32_t> bin_items;
+    DevBuf<BounceCtrl> ctrl;
+    uint32_t capacity = 0;
+    // parity scratch
+    DevBuf<float> scratch_f[8];
+    DevBuf<int32_t> scratch_i[2];
+    // display pipeline (pt_dispatch_ray)
+    DevBuf<float4> disp_color, disp_normal, disp_mix;
+    DevBuf<float> disp_depth;
+    DevBuf<uint8_t> disp_bgra;
+    int disp_w = 0, disp_h = 0;
+    // stats
+    pt_stats stats{};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> stage_events;
+    int grid_traverse = 0, grid_shade = 0;
+};
+
+namespace {
+
+// MotionalCamera::GetCopy, cuSrc/motional_camera.cu:177-200 (host math, fp32, no contraction)
+struct H3 { float x, y, z; };
+inline H3 h3(float x, float y, float z) { return H3{x, y, z}; }
+inline H3 hsub(H3 a, H3 b) { return h3(a.x - b.x, a.y - b.y, a.z - b.z); }
+inline H3 hadd(H3 a, H3 b) { return h3(a.x + b.x, a.y + b.y, a.z + b.z); }
+inline H3 hscale(H3 a, float s) { return h3(a.x * s, a.y * s, a.z * s); }
+inline float hdot(H3 a, H3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline H3 hcross(H3 a, H3 b) { return h3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+inline H3 hnormalize(H3 v) { float inv = 1.0f / sqrtf(hdot(v, v)); return hscale(v, inv); }
+
+struct HostCameraFrame { H3 u, v, w, top_left, horizontal, vertical; float dist; };
+
+HostCameraFrame camera_frame(const pt_camera* c) {
+    HostCameraFrame f;
+    H3 origin = h3(c->origin[0], c->origin[1], c->origin[2]);
+    H3 look_at = h3(c->look_at[0], c->look_at[1], c->look_at[2]);
+    H3 vup = h3(c->vup[0], c->vup[1], c->vup[2]);
+    float theta = (float)((double)c->view_fov_deg * 3.14159265358979323846 / 180);
+    float aspect = (float)c->width / (float)c->height;
+    float half_h = tanf(theta / 2);
+    float half_w = aspect * half_h;
+    f.w = hnormalize(hsub(origin, look_at));
+    f.u = hnormalize(hcross(vup, f.w));
+    f.v = hcross(f.w, f.u);
+    f.dist = sqrtf(hdot(hsub(origin, look_at), hsub(origin, look_at)));
+    f.top_left = hsub(hadd(hsub(origin, hscale(f.u, half_w * f.dist)), hscale(f.v, half_h * f.dist)), hscale(f.w, f.dist));
+    f.horizontal = hscale(f.u, 2 * half_w * f.dist);
+    f.vertical = hscale(f.v, -2 * half_h * f.dist);
+    return f;
+}
+
+CameraFrame to_device_frame(const pt_camera* c) {
+    HostCameraFrame h = camera_frame(c);
+    CameraFrame d;
+    d.origin = make_float3(c->origin[0], c->origin[1], c->origin[2]);
+    d.u = make_float3(h.u.x, h.u.y, h.u.z);
+    d.v = make_float3(h.v.x, h.v.y, h.v.z);
+    d.top_left = make_float3(h.top_left.x, h.top_left.y, h.top_left.z);
+    d.horizontal = make_float3(h.horizontal.x, h.horizontal.y, h.horizontal.z);
+    d.vertical = make_float3(h.vertical.x, h.vertical.y, h.vertical.z);
+    d.lens_radius = c->lens_radius;
+    d.width = c->width; d.height = c->height;
+    return d;
+}
+
+MaterialRec make_material_rec(const pt_material& m) {
+    MaterialRec r;
+    memset(&r, 0, sizeof(r));
+    r.kd[0] = m.kd[0]; r.kd[1] = m.kd[1]; r.kd[2] = m.kd[2];
+    r.emit = m.emit_intensity;
+    r.ior = m.refractive_index;
+    r.reflectivity = m.reflectivity;
+    r.type = m.type;
+    float alpha = powf(1000.0f, m.smoothness);       // material.cu:43,69,104
+    r.inv_alpha = 1.0 / (double)alpha;               // `1.0 / alpha` at material.cu:45,78,105
+    r.flags = (alpha >= 1e9f) ? PT_MATF_SPECULAR : 0;
+    r.tex = m.have_tex ? (unsigned long long)m.tex : 0ull;
+    return r;
+}
+
+int material_slot(pt_scene* s, const pt_material& m_in) {
+    MatKey k;
+    memset(&k.m, 0, sizeof(k.m));
+    k.m.type = m_in.type; k.m.have_tex = m_in.have_tex ? 1 : 0;
+    memcpy(k.m.kd, m_in.kd, sizeof(k.m.kd));
+    k.m.refractive_index = m_in.refractive_index; k.m.emit_intensity = m_in.emit_intensity;
+    k.m.smoothness = m_in.smoothness; k.m.reflectivity = m_in.reflectivity;
+    k.m.tex = m_in.have_tex ? m_in.tex : 0;
+    auto it = s->material_slots.find(k);
+    if (it != s->material_slots.end()) return it->second;
+    int slot = (int)s->materials.size();
+    s->materials.push_back(k.m);
+    s->material_slots[k] = slot;
+    return slot;
+}
+
+// The reference's leaf visiting order, needed only to resolve exactly tied hits the way it does.
+// Restates the *ordering* produced by SceneBVH::Divide (cuSrc/bvh.cu:31-90: sort the range by box centre
+// along the longest axis, split at the median index) and the right-son-first pop order of TraceRay
+// (bvh.cu:201-202): a leaf's rank is its position counted from the END of the final permutation.
+struct RefOrder {
+    const std::vector<HostPrim>& prims;
+    std::vector<float> mn, mx;   // 3 floats per prim, Object::GetAABBMin/Max (object.cu:134-170)
+    std::vector<int> order;
+    explicit RefOrder(const std::vector<HostPrim>& p) : prims(p) {
+        const float tol = PT_BOUNCE_TMIN * 5.f;
+        mn.resize(3 * p.size()); mx.resize(3 * p.size()); order.resize(p.size());
+        for (size_t i = 0; i < p.size(); ++i) {
+            const HostPrim& o = p[i];
+            float ar = o.radius >= 0 ? o.radius : -o.radius;
+            order[i] = (int)i;
+            if (o.type == PT_PRIM_SPHERE) {
+                for (int k = 0; k < 3; ++k) { mn[3 * i + k] = o.c[k] - ar; mx[3 * i + k] = o.c[k] + ar; }
+            } else if (o.type == PT_PRIM_PLATFORM) {
+                mn[3 * i] = -PT_TMAX * 5; mn[3 * i + 1] = o.y_pos - tol; mn[3 * i + 2] = -PT_TMAX * 5;
+                mx[3 * i] = PT_TMAX * 5;  mx[3 * i + 1] = o.y_pos + tol; mx[3 * i + 2] = PT_TMAX * 5;
+            } else {
+                mn[3 * i] = o.c[0] - ar; mn[3 * i + 1] = o.c[1] - o.height / 2 - tol; mn[3 * i + 2] = o.c[2] - ar;
+                mx[3 * i] = o.c[0] + ar; mx[3 * i + 1] = o.c[1] + o.height / 2 + tol; mx[3 * i + 2] = o.c[2] + ar;
+            }
+        }
+    }
+    void split(int l, int r) {
+        if (r - l < 2) return;
+        float lo[3], hi[3];
+        for (int k = 0; k < 3; ++k) { lo[k] = mn[3 * order[l] + k]; hi[k] = mx[3 * order[l] + k]; }
+        for (int i = l + 1; i < r; ++i)
+            for (int k = 0; k < 3; ++k) {
+                float a = mn[3 * order[i] + k], b = mx[3 * order[i] + k];
+                lo[k] = lo[k] < a ? lo[k] : a;
+                hi[k] = hi[k] > b ? hi[k] : b;
+            }
+        float sx = hi[0] - lo[0], sy = hi[1] - lo[1], sz = hi[2] - lo[2];
+        int axis = (sx >= sy && sx >= sz) ? 0 : (sy >= sz ? 1 : 2);
+        const float* MN = mn.data(); const float* MX = mx.data();
+        std::sort(order.begin() + l, order.begin() + r, [MN, MX, axis](int a, int b) {
+            return (MN[3 * a + axis] + MX[3 * a + axis]) / 2 < (MN[3 * b + axis] + MX[3 * b + axis]) / 2;
+        });
+        int mid = (l + r) / 2;
+        split(l, mid);
+        split(mid, r);
+    }
+    std::vector<uint32_t> ranks() {
+        split(0, (int)order.size());
+        std::vector<uint32_t> rk(order.size());
+        const size_t n = order.size();
+        for (size_t pos = 0; pos < n; ++pos) rk[order[pos]] = (uint32_t)(n - 1 - pos);
+        return rk;
+    }
+};
+
+int upload_and_build(pt_scene* s) {
+    const int n = (int)s->prims.size();
+    cudaStream_t st = s->stream;
+    std::vector<float4> g0(std::max(n, 1)), g1(std::max(n, 1));
+    std::vector<float> py; std::vector<int> pid, tree;
+    s->has_emitters = 0;
+    for (int i = 0; i < n; ++i) {
+        const HostPrim& p = s->prims[i];
+        const pt_material& m = s->materials[p.mat_slot];
+        if (m.emit_intensity != 0.f) s->has_emitters = 1;
+        uint32_t w = ((uint32_t)bin_of_material_type(m.type) << 28) | (uint32_t)p.mat_slot;
+        float wf, tf; int ty = p.type;
+        memcpy(&wf, &w, 4); memcpy(&tf, &ty, 4);
+        g0[i] = make_float4(p.c[0], p.c[1], p.c[2], p.radius);
+        g1[i] = make_float4(p.height, p.y_pos, tf, wf);
+        if (p.type == PT_PRIM_PLATFORM) { py.push_back(p.y_pos); pid.push_back(i); }
+        else if (p.type == PT_PRIM_SPHERE || p.type == PT_PRIM_CYLINDER) tree.push_back(i);
+    }
+    std::vector<MaterialRec> recs(std::max<size_t>(s->materials.size(), 1));
+    for (size_t i = 0; i < s->materials.size(); ++i) recs[i] = make_material_rec(s->materials[i]);
+    // tie ranks: only scenes with coplanar candidates (platforms / cylinders) can produce exact ties
+    std::vector<uint32_t> rank(std::max(n, 1));
+    bool need_ref_order = s->opt_tie_order && (int)tree.size() != n - (int)py.size() ? true : false;
+    int n_cyl = 0;
+    for (int i = 0; i < n; ++i) n_cyl += s->prims[i].type == PT_PRIM_CYLINDER;
+    need_ref_order = s->opt_tie_order && (n_cyl + (int)py.size() >= 2);
+    if (need_ref_order) rank = RefOrder(s->prims).ranks();
+    else for (int i = 0; i < n; ++i) rank[i] = (uint32_t)i;
+
+    CK(s->geo0.reserve(g0.size())); CK(s->geo1.reserve(g1.size())); CK(s->mats.reserve(recs.size()));
+    CK(s->tie_rank.reserve(rank.size()));
+    CK(s->plat_y.reserve(std::max<size_t>(py.size(), 1))); CK(s->plat_id.reserve(std::max<size_t>(pid.size(), 1)));
+    CK(cudaMemcpyAsync(s->geo0.p, g0.data(), g0.size() * sizeof(float4), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s->geo1.p, g1.data(), g1.size() * sizeof(float4), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s->mats.p, recs.data(), recs.size() * sizeof(MaterialRec), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s->tie_rank.p, rank.data(), rank.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    if (!py.empty()) {
+        CK(cudaMemcpyAsync(s->plat_y.p, py.data(), py.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(s->plat_id.p, pid.data(), pid.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    }
+    s->n_plat = (int)py.size();
+    s->n_tree = (int)tree.size();
+    const int nt = s->n_tree;
+    CK(cudaEventRecord(s->ev0, st));
+    if (nt > 0) {
+        CK(s->bvh_prims.reserve(nt));
+        CK(cudaMemcpyAsync(s->bvh_prims.p, tree.data(), nt * sizeof(int), cudaMemcpyHostToDevice, st));
+        CK(s->nodes.reserve(4 * (size_t)std::max(nt - 1, 1)));
+        if (nt == 1) {
+            k_lbvh_single<<<1, 1, 0, st>>>(s->bvh_prims.p, s->geo0.p, s->geo1.p, s->nodes.p);
+            s->stats.launches += 1;
+        } else {
+            CK(s->leaf_mn.reserve(nt)); CK(s->leaf_mx.reserve(nt)); CK(s->inner_mn.reserve(nt)); CK(s->inner_mx.reserve(nt));
+            CK(s->codes.reserve(nt)); CK(s->codes_sorted.reserve(nt)); CK(s->ids.reserve(nt)); CK(s->ids_sorted.reserve(nt));
+            CK(s->bounds6.reserve(8)); CK(s->children.reserve(nt)); CK(s->parent_inner.reserve(nt));
+            CK(s->parent_leaf.reserve(nt)); CK(s->flags.reserve(nt));
+            const uint32_t init6[8] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 0u, 0u};
+            CK(cudaMemcpyAsync(s->bounds6.p, init6, sizeof(init6), cudaMemcpyHostToDevice, st));
+            CK(cudaMemsetAsync(s->flags.p, 0, nt * sizeof(int), st));
+            const int tb = 256, gb = (nt + tb - 1) / tb;
+            k_lbvh_bounds<<<gb, tb, 0, st>>>(nt, s->bvh_prims.p, s->geo0.p, s->geo1.p, s->leaf_mn.p, s->leaf_mx.p, s->bounds6.p);
+            k_lbvh_morton<<<gb, tb, 0, st>>>(nt, s->leaf_mn.p, s->leaf_mx.p, s->bounds6.p, s->codes.p, s->ids.p);
+            size_t tmp_bytes = 0;
+            CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, s->codes.p, s->codes_sorted.p, s->ids.p, s->ids_sorted.p, nt, 0, 30, st));
+            CK(s->cub_tmp.reserve(tmp_bytes + 16));
+            CK(cub::DeviceRadixSort::SortPairs(s->cub_tmp.p, tmp_bytes, s->codes.p, s->codes_sorted.p, s->ids.p, s->ids_sorted.p, nt, 0, 30, st));
+            k_lbvh_hierarchy<<<gb, tb, 0, st>>>(nt, s->codes_sorted.p, s->children.p, s->parent_inner.p, s->parent_leaf.p);
+            k_lbvh_fit<<<gb, tb, 0, st>>>(nt, s->ids_sorted.p, s->leaf_mn.p, s->leaf_mx.p, s->children.p, s->parent_inner.p,
+                                          s->parent_leaf.p, s->inner_mn.p, s->inner_mx.p, s->flags.p);
+            k_lbvh_pack<<<gb, tb, 0, st>>>(nt, s->ids_sorted.p, s->bvh_prims.p, s->geo1.p, s->leaf_mn.p, s->leaf_mx.p,
+                                           s->children.p, s->inner_mn.p, s->inner_mx.p, s->nodes.p);
+            s->stats.launches += 5 + 2;   // + the radix sort's own kernels (library), counted as 2
+        }
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(s->ev1, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaEventElapsedTime(&s->stats.build_ms, s->ev0, s->ev1));
+    s->stats.bvh_nodes = nt > 1 ? (uint32_t)(nt - 1) : (uint32_t)nt;
+    s->dirty = false; s->built = true;
+    return PT_OK;
+}
+
+SceneDev scene_dev(pt_scene* s) {
+    SceneDev d;
+    d.nodes = s->nodes.p; d.geo0 = s->geo0.p; d.geo1 = s->geo1.p; d.mats = s->mats.p;
+    d.plat_y = s->plat_y.p; d.plat_id = s->plat_id.p; d.tie_rank = s->tie_rank.p;
+    d.n_plat = s->n_plat; d.n_tree_prims = s->n_tree; d.sky = s->sky.obj; d.has_emitters = s->has_emitters;
+    return d;
+}
+
+int ensure_sky(pt_scene* s) {
+    if (s->sky.obj) return PT_OK;
+    const uint8_t black[4] = {0, 0, 0, 255};
+    return pt_set_sky_rgba8(s, black, 1, 1);
+}
+
+int ensure_frame(pt_scene* s, int w, int h) {
+    if (w <= 0 || h <= 0 || (uint64_t)w * h > (1ull << 27)) return fail(PT_ERR_INVALID, "bad frame size");
+    if (w != s->width || h != s->height) {
+        s->accum.release();
+        CK(s->accum.reserve((size_t)w * h));
+        CK(cudaMemsetAsync(s->accum.p, 0, (size_t)w * h * sizeof(float4), s->stream));
+        s->width = w; s->height = h;
+    }
+    return PT_OK;
+}
+
+int ensure_queues(pt_scene* s, uint32_t cap, int max_depth) {
+    if (cap > s->capacity) {
+        for (int k = 0; k < 2; ++k) { CK(s->q_o[k].reserve(cap)); CK(s->q_d[k].reserve(cap)); CK(s->q_thr[k].reserve(cap)); }
+        CK(s->path_out.reserve(cap)); CK(s->hit.reserve(cap)); CK(s->bin_items.reserve((size_t)NUM_BINS * cap));
+        s->capacity = cap;
+    }
+    CK(s->ctrl.reserve((size_t)max_depth + 2));
+    return PT_OK;
+}
+
+int launch_config(pt_scene* s) {
+    if (s->grid_traverse) return PT_OK;
+    int occ_t = 0, occ_s = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, k_traverse<false>, 128, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_shade, 128, 0));
+    s->grid_traverse = s->sm_count * std::max(occ_t, 1);
+    s->grid_shade = s->sm_count * std::max(occ_s, 1);
+    return PT_OK;
+}
+
+int render_async(pt_scene* s, const pt_camera* cam, int spp, int max_depth, uint64_t seed, uint32_t first_sample) {
+    if (!s || !cam) return fail(PT_ERR_INVALID, "null argument");
+    if (!s->built || s->dirty) return fail(PT_ERR_NOT_BUILT, "pt_build must be called after the scene changed");
+    if (spp <= 0 || max_depth <= 0 || max_depth > 64) return fail(PT_ERR_INVALID, "bad spp / max_depth");
+    int rc = ensure_frame(s, cam->width, cam->height); if (rc) return rc;
+    rc = ensure_sky(s); if (rc) return rc;
+    rc = launch_config(s); if (rc) return rc;
+    const uint32_t npix = (uint32_t)cam->width * (uint32_t)cam->height;
+    uint32_t spp_per_wave = std::max<uint32_t>(1u, s->opt_wave_paths / npix);
+    spp_per_wave = std::min<uint32_t>(spp_per_wave, (uint32_t)spp);
+    const uint32_t cap = npix * spp_per_wave;
+    rc = ensure_queues(s, cap, max_depth); if (rc) return rc;
+    cudaStream_t st = s->stream;
+    const CameraFrame frame = to_device_frame(cam);
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    const SceneDev sd = scene_dev(s);
+    const bool timing = s->opt_stage_timing != 0;
+    size_t ev_i = 0;
+    auto stage_event = [&]() -> cudaError_t {
+        if (!timing) return cudaSuccess;
+        if (ev_i >= s->stage_events.size()) { cudaEvent_t e; cudaError_t r = cudaEventCreate(&e); if (r) return r; s->stage_events.push_back(e); }
+        return cudaEventRecord(s->stage_events[ev_i++], st);
+    };
+    CK(cudaEventRecord(s->ev0, st));
+    uint64_t launches = 0;
+    for (uint32_t s0 = 0; s0 < (uint32_t)spp; s0 += spp_per_wave) {
+        const uint32_t ns = std::min<uint32_t>(spp_per_wave, (uint32_t)spp - s0);
+        const uint32_t n_paths = npix * ns;
+        CK(cudaMemsetAsync(s->ctrl.p, 0, ((size_t)max_depth + 2) * sizeof(BounceCtrl), st));
+        const int rg_grid = (int)std::min<uint32_t>((n_paths + 255u) / 256u, (uint32_t)s->sm_count * 16u);
+        k_raygen<<<rg_grid, 256, 0, st>>>(frame, key, npix, n_paths, first_sample + s0, s->q_o[0].p, s->q_d[0].p,
+                                          s->q_thr[0].p, s->path_out.p, s->has_emitters, s->ctrl.p);
+        ++launches;
+        int cur = 0;
+        for (int b = 0; b < max_depth; ++b) {
+            CK(stage_event());
+            k_traverse<false><<<s->grid_traverse, 128, 0, st>>>(sd, s->q_o[cur].p, s->q_d[cur].p, nullptr,
+                                                               b == 0 ? 0.f : PT_BOUNCE_TMIN, s->ctrl.p + b, s->hit.p,
+                                                               s->bin_items.p, s->capacity);
+            CK(stage_event());
+            k_shade<<<s->grid_shade, 128, 0, st>>>(sd, key, npix, first_sample + s0, b, max_depth, s->q_o[cur].p,
+                                                   s->q_d[cur].p, s->q_thr[cur].p, s->hit.p, s->bin_items.p, s->capacity,
+                                                   s->ctrl.p + b, s->ctrl.p + b + 1, s->q_o[cur ^ 1].p, s->q_d[cur ^ 1].p,
+                                                   s->q_thr[cur ^ 1].p, s->path_out.p);
+            launches += 2;
+            cur ^= 1;
+        }
+        CK(stage_event());
+        const int ac_grid = (int)std::min<uint32_t>((npix + 255u) / 256u, (uint32_t)s->sm_count * 8u);
+        k_accumulate<<<ac_grid, 256, 0, st>>>(npix, ns, s->path_out.p, s->accum.p);
+        ++launches;
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(s->ev1, st));
+    s->stats.launches += launches;
+    s->stats.paths = (uint64_t)npix * (uint64_t)spp;
+    s->stats.wave_paths = cap;
+    s->stats.segments = 0;
+    return PT_OK;
+}
+
+int finish_frame(pt_scene* s, int max_depth_hint) {
+    (void)max_depth_hint;
+    CK(cudaStreamSynchronize(s->stream));
+    CK(cudaEventElapsedTime(&s->stats.render_ms, s->ev0, s->ev1));
+    return PT_OK;
+}
+
+template <class T>
+int to_device(DevBuf<T>& buf, const T* host, size_t n, cudaStream_t st) {
+    CK(buf.reserve(std::max<size_t>(n, 1)));
+    if (n) CK(cudaMemcpyAsync(buf.p, host, n * sizeof(T), cudaMemcpyHostToDevice, st));
+    return PT_OK;
+}
+
+// ---- small kernels behind the parity entry points (same device functions as the render stages) ----
+__global__ void k_pack_rays(int n, const float* __restrict__ rays8, float4* __restrict__ ray_o, float4* __restrict__ ray_d,
+                            float2* __restrict__ range, BounceCtrl* __restrict__ ctrl) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) ctrl->in_count = (uint32_t)n;
+    if (i >= n) return;
+    ray_o[i] = make_float4(rays8[8 * i], rays8[8 * i + 1], rays8[8 * i + 2], __uint_as_float((uint32_t)i));
+    ray_d[i] = make_float4(rays8[8 * i + 3], rays8[8 * i + 4], rays8[8 * i + 5], 0.f);
+    range[i] = make_float2(rays8[8 * i + 6], rays8[8 * i + 7]);
+}
+__global__ void k_unpack_hits(int n, SceneDev sc, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
+                              const uint2* __restrict__ hit, int32_t* __restrict__ prim, float* __restrict__ t,
+                              float* __restrict__ normal3, float* __restrict__ pos3) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint2 h = hit[i];
+    float3 pos = f3(0, 0, 0), nrm = f3(0, 0, 0);
+    if (h.y == PT_MISS_CODE) prim[i] = -1;
+    else {
+        prim[i] = (int32_t)(h.y >> 3);
+        float4 o = ray_o[i], d = ray_d[i];
+        hit_attributes(sc.geo0[h.y >> 3], (int)(h.y & 7u), f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), __uint_as_float(h.x), pos, nrm);
+    }
+    t[i] = __uint_as_float(h.x);
+    normal3[3 * i] = nrm.x; normal3[3 * i + 1] = nrm.y; normal3[3 * i + 2] = nrm.z;
+    pos3[3 * i] = pos.x; pos3[3 * i + 1] = pos.y; pos3[3 * i + 2] = pos.z;
+}
+__global__ void k_shade_batch(int n, const MaterialRec* __restrict__ mats, const int32_t* __restrict__ mat_idx,
+                              const float* __restrict__ nrm3, const float* __restrict__ in3, const float* __restrict__ u3,
+                              float* __restrict__ bounce3, float* __restrict__ atten3, float* __restrict__ rad3,
+                              int32_t* __restrict__ ndraws) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const MaterialRec m = mats[mat_idx[i]];
+    Scatter s;
+    shade_bin(bin_of_material_type(m.type), m, f3(nrm3[3 * i], nrm3[3 * i + 1], nrm3[3 * i + 2]),
+              f3(in3[3 * i], in3[3 * i + 1], in3[3 * i + 2]), make_float4(u3[3 * i], u3[3 * i + 1], u3[3 * i + 2], 0.f), s);
+    bounce3[3 * i] = s.bounce.x; bounce3[3 * i + 1] = s.bounce.y; bounce3[3 * i + 2] = s.bounce.z;
+    atten3[3 * i] = s.atten.x; atten3[3 * i + 1] = s.atten.y; atten3[3 * i + 2] = s.atten.z;
+    rad3[3 * i] = s.radiance.x; rad3[3 * i + 1] = s.radiance.y; rad3[3 * i + 2] = s.radiance.z;
+    ndraws[i] = s.draws;
+}
+__global__ void k_raygen_batch(int n, CameraFrame cam, const int32_t* __restrict__ xy, const float* __restrict__ u3,
+                               float* __restrict__ rays8) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float3 o, d;
+    camera_ray(cam, xy[2 * i], xy[2 * i + 1], make_float4(u3[3 * i], u3[3 * i + 1], u3[3 * i + 2], 0.f), o, d);
+    rays8[8 * i] = o.x; rays8[8 * i + 1] = o.y; rays8[8 * i + 2] = o.z;
+    rays8[8 * i + 3] = d.x; rays8[8 * i + 4] = d.y; rays8[8 * i + 5] = d.z;
+    rays8[8 * i + 6] = 0.f; rays8[8 * i + 7] = PT_TMAX;
+}
+__global__ void k_sky_batch(int n, cudaTextureObject_t sky, const float* __restrict__ dir3, float* __restrict__ rgb3) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float3 c = sky_radiance(sky, f3(dir3[3 * i], dir3[3 * i + 1], dir3[3 * i + 2]));
+    rgb3[3 * i] = c.x; rgb3[3 * i + 1] = c.y; rgb3[3 * i + 2] = c.z;
+}
+__global__ void k_philox_batch(int n, uint2 key, const uint32_t* __restrict__ pss, float* __restrict__ u4) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 u = philox_uniform4(key, pss[3 * i], pss[3 * i + 1], pss[3 * i + 2]);
+    u4[4 * i] = u.x; u4[4 * i + 1] = u.y; u4[4 * i + 2] = u.z; u4[4 * i + 3] = u.w;
+}
+__global__ void k_read_accum(uint32_t npix, const float4* __restrict__ accum, float4* __restrict__ out) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    float4 a = accum[p];
+    float n = a.w > 0.f ? a.w : 1.f;
+    out[p] = make_float4(a.x / n, a.y / n, a.z / n, a.w);
+}
+
+int create_texture(const uint8_t* rgba, int w, int h, size_t row_bytes, Texture& out, cudaStream_t st) {
+    if (!rgba || w <= 0 || h <= 0) return fail(PT_ERR_INVALID, "bad texture");
+    cudaChannelFormatDesc desc = cudaCreateChannelDesc<uchar4>();
+    Texture t;
+    CK(cudaMallocArray(&t.arr, &desc, w, h));
+    // the array is first cleared so that texels the reference leaves uninitialised (textures.cu:32) read as 0
+    std::vector<uint8_t> staged((size_t)w * h * 4, 0);
+    for (int y = 0; y < h; ++y) memcpy(&staged[(size_t)y * w * 4], rgba + (size_t)y * w * 4, row_bytes);
+    CK(cudaMemcpy2DToArrayAsync(t.arr, 0, 0, staged.data(), (size_t)w * 4, (size_t)w * 4, h, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    cudaResourceDesc rd; memset(&rd, 0, sizeof(rd));
+    rd.resType = cudaResourceTypeArray; rd.res.array.array = t.arr;
+    cudaTextureDesc td; memset(&td, 0, sizeof(td));       // textures.cu:46-50
+    td.addressMode[0] = cudaAddressModeMirror; td.addressMode[1] = cudaAddressModeMirror;
+    td.filterMode = cudaFilterModeLinear; td.readMode = cudaReadModeNormalizedFloat; td.normalizedCoords = 1;
+    CK(cudaCreateTextureObject(&t.obj, &rd, &td, nullptr));
+    out = t;
+    return PT_OK;
+}
+void destroy_texture(Texture& t) {
+    if (t.obj) cudaDestroyTextureObject(t.obj);
+    if (t.arr) cudaFreeArray(t.arr);
+    t.obj = 0; t.arr = nullptr;
+}
+
+int display_dispatch(pt_scene*, const pt_camera*, int, uint64_t, uint32_t, uint8_t*, size_t) {
+    return fail(PT_ERR_INVALID, "pt_dispatch_ray: display pipeline not built yet");
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* pt_last_error(void) { return g_err.c_str(); }
+const char* pt_version(void) { return "cpppathtracer_b200 0.1 (sm_100a wavefront)"; }
+
+int pt_scene_create(pt_scene** out) {
+    if (!out) return fail(PT_ERR_INVALID, "null out");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(PT_ERR_NO_DEVICE, std::string("no CUDA device (this library has no CPU path): ") + cudaGetErrorString(e));
+    pt_scene* s = new pt_scene();
+    CK(cudaGetDevice(&s->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, s->device));
+    s->sm_count = prop.multiProcessorCount;
+    CK(cudaEventCreate(&s->ev0)); CK(cudaEventCreate(&s->ev1));
+    *out = s;
+    return PT_OK;
+}
+
+void pt_scene_destroy(pt_scene* s) {
+    if (!s) return;
+    cudaStreamSynchronize(s->stream);
+    destroy_texture(s->sky);
+    for (auto& kv : s->textures) destroy_texture(kv.second);
+    s->geo0.release(); s->geo1.release(); s->nodes.release(); s->leaf_mn.release(); s->leaf_mx.release();
+    s->inner_mn.release(); s->inner_mx.release(); s->mats.release(); s->plat_y.release(); s->plat_id.release();
+    s->bvh_prims.release(); s->parent_inner.release(); s->parent_leaf.release(); s->flags.release(); s->children.release();
+    s->codes.release(); s->codes_sorted.release(); s->ids.release(); s->ids_sorted.release(); s->bounds6.release();
+    s->tie_rank.release(); s->cub_tmp.release(); s->accum.release(); s->path_out.release(); s->hit.release();
+    s->bin_items.release(); s->ctrl.release();
+    for (int k = 0; k < 2; ++k) { s->q_o[k].release(); s->q_d[k].release(); s->q_thr[k].release(); s->scratch_i[k].release(); }
+    for (auto& b : s->scratch_f) b.release();
+    s->disp_color.release(); s->disp_normal.release(); s->disp_mix.release(); s->disp_depth.release(); s->disp_bgra.release();
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    for (auto e : s->stage_events) cudaEventDestroy(e);
+    delete s;
+}
+
+int pt_set_option(pt_scene* s, int option, int64_t value) {
+    if (!s) return fail(PT_ERR_INVALID, "null scene");
+    switch (option) {
+        case PT_OPT_WAVE_PATHS:
+            if (value < 1024 || value > (1ll << 28)) return fail(PT_ERR_INVALID, "wave_paths out of range");
+            s->opt_wave_paths = (uint32_t)value; return PT_OK;
+        case PT_OPT_STAGE_TIMING: s->opt_stage_timing = value != 0; return PT_OK;
+        case PT_OPT_TIE_ORDER: s->opt_tie_order = value != 0; s->dirty = true; return PT_OK;
+        case PT_OPT_SKY_QUARTER_ROWS: s->opt_sky_quarter = value != 0; return PT_OK;
+        default: return fail(PT_ERR_INVALID, "unknown option");
+    }
+}
+
+int pt_set_stream(pt_scene* s, void* cuda_stream) {
+    if (!s) return fail(PT_ERR_INVALID, "null scene");
+    s->stream = (cudaStream_t)cuda_stream;
+    return PT_OK;
+}
+
+static int add_prim(pt_scene* s, int type, const float* c, float radius, float y_pos, float height) {
+    if (!s) return fail(PT_ERR_INVALID, "null scene");
+    if (s->prims.size() >= (1u << 28)) return fail(PT_ERR_INVALID, "too many primitives");
+    HostPrim p;
+    p.type = type;
+    p.c[0] = c ? c[0] : 0.f; p.c[1] = c ? c[1] : 0.f; p.c[2] = c ? c[2] : 0.f;
+    p.radius = radius; p.y_pos = y_pos; p.height = height;
+    pt_material zero; memset(&zero, 0, sizeof(zero));   // the caller memsets Object to 0 (video_renderer.cpp:75,85)
+    p.mat_slot = material_slot(s, zero);
+    s->prims.push_back(p);
+    s->dirty = true;
+    return (int)s->prims.size() - 1;
+}
+int pt_add_sphere(pt_scene* s, const float center[3], float radius) {
+    if (!center) return fail(PT_ERR_INVALID, "null center");
+    return add_prim(s, PT_PRIM_SPHERE, center, radius, 0.f, 0.f);
+}
+int pt_add_platform(pt_scene* s, float y_pos) { return add_prim(s, PT_PRIM_PLATFORM, nullptr, 0.f, y_pos, 0.f); }
+int pt_add_cylinder(pt_scene* s, const float center[3], float radius, float height) {
+    if (!center) return fail(PT_ERR_INVALID, "null center");
+    return add_prim(s, PT_PRIM_CYLINDER, center, radius, 0.f, height);
+}
+int pt_set_material(pt_scene* s, int prim, const pt_material* m) {
+    if (!s || !m) return fail(PT_ERR_INVALID, "null argument");
+    if (prim < 0 || prim >= (int)s->prims.size()) return fail(PT_ERR_INVALID, "primitive id out of range");
+    s->prims[prim].mat_slot = material_slot(s, *m);
+    s->dirty = true;
+    return PT_OK;
+}
+int pt_update_prim(pt_scene* s, int prim, const float center[3], float radius, float y_pos, float height) {
+    if (!s) return fail(PT_ERR_INVALID, "null scene");
+    if (prim < 0 || prim >= (int)s->prims.size()) return fail(PT_ERR_INVALID, "primitive id out of range");
+    HostPrim& p = s->prims[prim];
+    if (center) { p.c[0] = center[0]; p.c[1] = center[1]; p.c[2] = center[2]; }
+    p.radius = radius; p.y_pos = y_pos; p.height = height;
+    s->dirty = true;
+    return PT_OK;
+}
+
+int pt_set_sky_rgba8(pt_scene* s, const uint8_t* rgba, int width, int height) {
+    if (!s) return fail(PT_ERR_INVALID, "null scene");
+    CK(cudaStreamSynchronize(s->stream));
+    destroy_texture(s->sky);
+    size_t row_bytes = s->opt_sky_quarter ? (size_t)width : (size_t)width * 4;
+    return create_texture(rgba, width, height, row_bytes, s->sky, s->stream);
+}
+
+int pt_texture_create_rgba8(pt_scene* s, const uint8_t* rgba, int width, int height, uint64_t* handle) {
+    if (!s || !handle) return fail(PT_ERR_INVALID, "null argument");
+    Texture t;
+    int rc = create_texture(rgba, width, height, (size_t)width * 4, t, s->stream);
+    if (rc) return rc;
+    s->textures[(uint64_t)t.obj] = t;
+    *handle = (uint64_t)t.obj;
+    return PT_OK;
+}
+int pt_texture_destroy(pt_scene* s, uint64_t handle) {
+    if (!s) return fail(PT_ERR_INVALID, "null scene");
+    auto it = s->textures.find(handle);
+    if (it == s->textures.end()) return fail(PT_ERR_INVALID, "unknown texture");
+    cudaStreamSynchronize(s->stream);
+    destroy_texture(it->second);
+    s->textures.erase(it);
+    return PT_OK;
+}
+
+int pt_build(pt_scene* s) {
+    if (!s) return fail(PT_ERR_INVALID, "null scene");
+    return upload_and_build(s);
+}
+
+int pt_render_frame_async(pt_scene* s, const pt_camera* cam, int spp, int max_depth, uint64_t seed, uint32_t first_sample) {
+    return render_async(s, cam, spp, max_depth, seed, first_sample);
+}
+int pt_synchronize(pt_scene* s) {
+    if (!s) return fail(PT_ERR_INVALID, "null scene");
+    return finish_frame(s, 0);
+}
+int pt_render_frame(pt_scene* s, const pt_camera* cam, int spp, int max_depth, uint64_t seed, uint32_t first_sample) {
+    int rc = render_async(s, cam, spp, max_depth, seed, first_sample);
+    if (rc) return rc;
+    rc = finish_frame(s, max_depth);
+    if (rc) return rc;
+    // segments traced = sum of the input queue sizes of every bounce of the LAST wave (diagnostic only)
+    std::vector<BounceCtrl> c((size_t)max_depth + 1);
+    CK(cudaMemcpy(c.data(), s->ctrl.p, c.size() * sizeof(BounceCtrl), cudaMemcpyDeviceToHost));
+    uint64_t seg = 0;
+    for (int b = 0; b < max_depth; ++b) seg += c[b].in_count;
+    s->stats.segments = seg;
+    if (s->opt_stage_timing && s->stage_events.size() >= 2) {
+        // events alternate: [traverse start, shade start] per bounce, then accumulate start, per wave
+        float trav = 0.f, shade = 0.f;
+        const size_t per_wave = 2 * (size_t)max_depth + 1;
+        for (size_t w0 = 0; w0 + per_wave <= s->stage_events.size(); w0 += per_wave)
+            for (int b = 0; b < max_depth; ++b) {
+                float a = 0.f, bms = 0.f;
+                cudaEventElapsedTime(&a, s->stage_events[w0 + 2 * b], s->stage_events[w0 + 2 * b + 1]);
+                cudaEventElapsedTime(&bms, s->stage_events[w0 + 2 * b + 1], s->stage_events[w0 + 2 * b + 2]);
+                trav += a; shade += bms;
+            }
+        s->stats.traverse_ms = trav; s->stats.shade_ms = shade;
+    }
+    return PT_OK;
+}
+
+int pt_reset_accum(pt_scene* s) {
+    if (!s) return fail(PT_ERR_INVALID, "null scene");
+    if (s->accum.p) CK(cudaMemsetAsync(s->accum.p, 0, (size_t)s->width * s->height * sizeof(float4), s->stream));
+    return PT_OK;
+}
+
+int pt_read_accum(pt_scene* s, float* rgba, size_t nfloats) {
+    if (!s || !rgba) return fail(PT_ERR_INVALID, "null argument");
+    const size_t npix = (size_t)s->width * s->height;
+    if (npix == 0 || nfloats != 4 * npix) return fail(PT_ERR_INVALID, "nfloats must be 4*width*height of the last frame");
+    DevBuf<float4> tmp;
+    CK(tmp.reserve(npix));
+    k_read_accum<<<(unsigned)((npix + 255) / 256), 256, 0, s->stream>>>((uint32_t)npix, s->accum.p, tmp.p);
+    s->stats.launches += 1;
+    cudaError_t e = cudaMemcpyAsync(rgba, tmp.p, npix * sizeof(float4), cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    tmp.release();
+    CK(e);
+    return PT_OK;
+}
+
+int pt_accum_device_ptr(pt_scene* s, float** dptr, size_t* nfloats) {
+    if (!s || !dptr || !nfloats) return fail(PT_ERR_INVALID, "null argument");
+    if (!s->accum.p) return fail(PT_ERR_INVALID, "no frame rendered yet");
+    *dptr = (float*)s->accum.p; *nfloats = 4 * (size_t)s->width * s->height;
+    return PT_OK;
+}
+
+int pt_get_stats(pt_scene* s, pt_stats* out) {
+    if (!s || !out) return fail(PT_ERR_INVALID, "null argument");
+    *out = s->stats;
+    return PT_OK;
+}
+
+int pt_trace_rays(pt_scene* s, int n, const float* rays8, int32_t* prim, float* t, float* normal3, float* hitpos3) {
+    if (!s || !rays8 || n < 0) return fail(PT_ERR_INVALID, "bad argument");
+    if (!s->built || s->dirty) return fail(PT_ERR_NOT_BUILT, "pt_build must be called after the scene changed");
+    if (n == 0) return PT_OK;
+    int rc = ensure_queues(s, (uint32_t)n, 1); if (rc) return rc;
+    rc = ensure_sky(s); if (rc) return rc;
+    rc = launch_config(s); if (rc) return rc;
+    cudaStream_t st = s->stream;
+    rc = to_device(s->scratch_f[0], rays8, (size_t)8 * n, st); if (rc) return rc;
+    CK(s->scratch_f[1].reserve((size_t)2 * n)); CK(s->scratch_f[2].reserve(n)); CK(s->scratch_f[3].reserve((size_t)3 * n));
+    CK(s->scratch_f[4].reserve((size_t)3 * n)); CK(s->scratch_i[0].reserve(n));
+    CK(cudaMemsetAsync(s->ctrl.p, 0, 2 * sizeof(BounceCtrl), st));
+    const int g = (n + 255) / 256;
+    k_pack_rays<<<g, 256, 0, st>>>(n, s->scratch_f[0].p, s->q_o[0].p, s->q_d[0].p, (float2*)s->scratch_f[1].p, s->ctrl.p);
+    k_traverse<true><<<s->grid_traverse, 128, 0, st>>>(scene_dev(s), s->q_o[0].p, s->q_d[0].p, (const float2*)s->scratch_f[1].p,
+                                                      0.f, s->ctrl.p, s->hit.p, s->bin_items.p, s->capacity);
+    k_unpack_hits<<<g, 256, 0, st>>>(n, scene_dev(s), s->q_o[0].p, s->q_d[0].p, s->hit.p, s->scratch_i[0].p,
+                                     s->scratch_f[2].p, s->scratch_f[3].p, s->scratch_f[4].p);
+    s->stats.launches += 3;
+    CK(cudaGetLastError());
+    if (prim) CK(cudaMemcpyAsync(prim, s->scratch_i[0].p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    if (t) CK(cudaMemcpyAsync(t, s->scratch_f[2].p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    if (normal3) CK(cudaMemcpyAsync(normal3, s->scratch_f[3].p, (size_t)n * 12, cudaMemcpyDeviceToHost, st));
+    if (hitpos3) CK(cudaMemcpyAsync(hitpos3, s->scratch_f[4].p, (size_t)n * 12, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return PT_OK;
+}
+
+int pt_shade_batch(pt_scene* s, int n, const pt_material* mats, int n_mats, const int32_t* mat_idx, const float* pos3,
+                   const float* normal3, const float* in_dir3, const float* u3, float* bounce3, float* atten3,
+                   float* radiance3, int32_t* n_draws) {
+    (void)pos3;
+    if (!s || !mats || !mat_idx || !normal3 || !in_dir3 || !u3 || n < 0 || n_mats <= 0) return fail(PT_ERR_INVALID, "bad argument");
+    if (n == 0) return PT_OK;
+    for (int i = 0; i < n; ++i) if (mat_idx[i] < 0 || mat_idx[i] >= n_mats) return fail(PT_ERR_INVALID, "mat_idx out of range");
+    cudaStream_t st = s->stream;
+    std::vector<MaterialRec> recs(n_mats);
+    for (int i = 0; i < n_mats; ++i) recs[i] = make_material_rec(mats[i]);
+    DevBuf<MaterialRec> dm;
+    int rc = to_device(dm, recs.data(), recs.size(), st); if (rc) return rc;
+    rc = to_device(s->scratch_i[0], mat_idx, n, st); if (rc) { dm.release(); return rc; }
+    rc = to_device(s->scratch_f[0], normal3, (size_t)3 * n, st); if (rc) { dm.release(); return rc; }
+    rc = to_device(s->scratch_f[1], in_dir3, (size_t)3 * n, st); if (rc) { dm.release(); return rc; }
+    rc = to_device(s->scratch_f[2], u3, (size_t)3 * n, st); if (rc) { dm.release(); return rc; }
+    cudaError_t e = cudaSuccess;
+    for (int k = 3; k < 6 && e == cudaSuccess; ++k) e = s->scratch_f[k].reserve((size_t)3 * n);
+    if (e == cudaSuccess) e = s->scratch_i[1].reserve(n);
+    if (e == cudaSuccess) {
+        k_shade_batch<<<(n + 127) / 128, 128, 0, st>>>(n, dm.p, s->scratch_i[0].p, s->scratch_f[0].p, s->scratch_f[1].p,
+                                                       s->scratch_f[2].p, s->scratch_f[3].p, s->scratch_f[4].p,
+                                                       s->scratch_f[5].p, s->scratch_i[1].p);
+        s->stats.launches += 1;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess && bounce3) e = cudaMemcpyAsync(bounce3, s->scratch_f[3].p, (size_t)n * 12, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && atten3) e = cudaMemcpyAsync(atten3, s->scratch_f[4].p, (size_t)n * 12, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && radiance3) e = cudaMemcpyAsync(radiance3, s->scratch_f[5].p, (size_t)n * 12, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && n_draws) e = cudaMemcpyAsync(n_draws, s->scratch_i[1].p, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    dm.release();
+    CK(e);
+    return PT_OK;
+}
+
+int pt_raygen_batch(pt_scene* s, const pt_camera* cam, int n, const int32_t* xy, const float* u3, float* rays8) {
+    if (!s || !cam || !xy || !u3 || !rays8 || n < 0) return fail(PT_ERR_INVALID, "bad argument");
+    if (n == 0) return PT_OK;
+    cudaStream_t st = s->stream;
+    int rc = to_device(s->scratch_i[0], xy, (size_t)2 * n, st); if (rc) return rc;
+    rc = to_device(s->scratch_f[0], u3, (size_t)3 * n, st); if (rc) return rc;
+    CK(s->scratch_f[1].reserve((size_t)8 * n));
+    k_raygen_batch<<<(n + 127) / 128, 128, 0, st>>>(n, to_device_frame(cam), s->scratch_i[0].p, s->scratch_f[0].p, s->scratch_f[1].p);
+    s->stats.launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(rays8, s->scratch_f[1].p, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return PT_OK;
+}
+
+int pt_sky_lookup(pt_scene* s, int n, const float* dir3, float* rgb3) {
+    if (!s || !dir3 || !rgb3 || n < 0) return fail(PT_ERR_INVALID, "bad argument");
+    if (n == 0) return PT_OK;
+    int rc = ensure_sky(s); if (rc) return rc;
+    cudaStream_t st = s->stream;
+    rc = to_device(s->scratch_f[0], dir3, (size_t)3 * n, st); if (rc) return rc;
+    CK(s->scratch_f[1].reserve((size_t)3 * n));
+    k_sky_batch<<<(n + 127) / 128, 128, 0, st>>>(n, s->sky.obj, s->scratch_f[0].p, s->scratch_f[1].p);
+    s->stats.launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(rgb3, s->scratch_f[1].p, (size_t)n * 12, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return PT_OK;
+}
+
+int pt_philox_uniforms(pt_scene* s, int n, uint64_t seed, const uint32_t* pss, float* u4) {
+    if (!s || !pss || !u4 || n < 0) return fail(PT_ERR_INVALID, "bad argument");
+    if (n == 0) return PT_OK;
+    cudaStream_t st = s->stream;
+    DevBuf<uint32_t> d;
+    int rc = to_device(d, pss, (size_t)3 * n, st); if (rc) return rc;
+    cudaError_t e = s->scratch_f[0].reserve((size_t)4 * n);
+    if (e == cudaSuccess) {
+        k_philox_batch<<<(n + 127) / 128, 128, 0, st>>>(n, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), d.p, s->scratch_f[0].p);
+        s->stats.launches += 1;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(u4, s->scratch_f[0].p, (size_t)n * 16, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    d.release();
+    CK(e);
+    return PT_OK;
+}
+
+int pt_camera_basis(const pt_camera* cam, float out19[19]) {
+    if (!cam || !out19) return fail(PT_ERR_INVALID, "null argument");
+    HostCameraFrame f = camera_frame(cam);
+    const H3* v[6] = {&f.u, &f.v, &f.w, &f.top_left, &f.horizontal, &f.vertical};
+    for (int k = 0; k < 6; ++k) { out19[3 * k] = v[k]->x; out19[3 * k + 1] = v[k]->y; out19[3 * k + 2] = v[k]->z; }
+    out19[18] = f.dist;
+    return PT_OK;
+}
+
+int pt_dispatch_ray(pt_scene* s, const pt_camera* cam, int max_depth, uint64_t seed, uint32_t sample_idx,
+                    uint8_t* bgra_out, size_t nbytes) {
+    return display_dispatch(s, cam, max_depth, seed, sample_idx, bgra_out, nbytes);
+}
+
+}  // extern "C"

@@ -1,0 +1,159 @@
+/*
+ * pt_api.h -- C ABI of the B200-native render path (libpt_b200.so).
+ *
+ * Drop-in boundary for the render hot path of DearPoca/CppPathTracer: everything the reference's
+ * `PathTracer` (include/path_tracer.h:15-26) does between "objects + camera in" and "pixels out"
+ * is behind these entry points.  Plain pointers and sizes only; the caller owns every host buffer,
+ * the library owns every device buffer.  All calls are synchronous unless stated, thread-compatible
+ * (one caller per scene) and return PT_OK (0) or a negative pt_status; pt_last_error() gives the text.
+ *
+ * Reference paths below are relative to the reference repository root.
+ */
+#ifndef PT_API_H
+#define PT_API_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pt_scene pt_scene;
+
+typedef enum pt_status {
+    PT_OK = 0,
+    PT_ERR_INVALID = -1,   /* bad argument / bad handle / call order            */
+    PT_ERR_CUDA = -2,      /* a CUDA runtime call failed (text in pt_last_error) */
+    PT_ERR_NOT_BUILT = -3, /* render / trace before pt_build                     */
+    PT_ERR_NO_DEVICE = -4  /* no CUDA device: this library has no CPU fallback   */
+} pt_status;
+
+/* PrimitiveType::Enum, include/object.h:7-15 */
+enum { PT_PRIM_SPHERE = 0, PT_PRIM_PLATFORM = 1, PT_PRIM_CYLINDER = 2 };
+/* MaterialType::Enum, include/material.h:5-15.  As in the reference's dispatcher
+ * (cuSrc/material.cu:151-156) type METAL runs the glossy-lobe "Mirror" shader and type MIRROR runs
+ * the reflectivity-mixing "Metal" shader; TEST and unknown values shade as DIFFUSE. */
+enum { PT_MAT_DIFFUSE = 0, PT_MAT_METAL = 1, PT_MAT_MIRROR = 2, PT_MAT_GLASS = 3, PT_MAT_TEST = 4 };
+
+/* class Material, include/material.h:17-35 (same fields, same meaning) */
+typedef struct pt_material {
+    int32_t type;
+    int32_t have_tex;       /* 1: kd is read from texture `tex` at (0,0) (material.cu:11-18) */
+    float kd[3];
+    float refractive_index;
+    float emit_intensity;
+    float smoothness;
+    float reflectivity;
+    uint64_t tex;           /* handle from pt_texture_create_rgba8 */
+} pt_material;
+
+/* The caller-visible state of class MotionalCamera (include/motional_camera.h:8-19) that
+ * MotionalCamera::GetCopy (cuSrc/motional_camera.cu:177-200) turns into a frame basis. */
+typedef struct pt_camera {
+    int32_t width, height;
+    float origin[3];
+    float look_at[3];
+    float vup[3];
+    float view_fov_deg;
+    float lens_radius;
+} pt_camera;
+
+typedef struct pt_stats {
+    uint64_t paths;           /* (pixel, sample) pairs traced by the last pt_render_frame     */
+    uint64_t segments;        /* rays (path segments) traced                                  */
+    uint64_t launches;        /* kernels launched by this scene since creation                */
+    float    render_ms;       /* device time of the last pt_render_frame (CUDA events)        */
+    float    traverse_ms;     /* ... of which closest-hit traversal (only with PT_OPT_STAGE_TIMING) */
+    float    shade_ms;        /* ... shade + miss                                             */
+    float    build_ms;        /* device time of the last pt_build                             */
+    uint32_t bvh_nodes;
+    uint32_t wave_paths;      /* paths in flight per wave                                     */
+} pt_stats;
+
+enum {
+    PT_OPT_WAVE_PATHS = 1,    /* upper bound of paths in flight per wave (default 16 Mi)           */
+    PT_OPT_STAGE_TIMING = 2,  /* 1: record per-stage CUDA events (adds syncs at frame end only)    */
+    PT_OPT_TIE_ORDER = 3,     /* 1 (default): exactly tied hits resolve in the reference's leaf
+                                 visiting order (bvh.cu:31-90,167-205); 0: lowest primitive id wins */
+    PT_OPT_SKY_QUARTER_ROWS = 4 /* 1 (default): reproduce the reference's upload that copies `width`
+                                 BYTES per row (cuSrc/textures.cu:32); 0: upload whole rows         */
+};
+
+/* ---- lifetime -------------------------------------------------------------------------------- */
+/* replaces `new PathTracer` (cppSrc/video_renderer.cpp:33).  Uses the calling thread's current CUDA
+ * device; fails with PT_ERR_NO_DEVICE when there is none. */
+int pt_scene_create(pt_scene** out);
+void pt_scene_destroy(pt_scene* s);
+int pt_set_option(pt_scene* s, int option, int64_t value);
+/* all work of this scene is enqueued on `cuda_stream` (a cudaStream_t; NULL = default stream) */
+int pt_set_stream(pt_scene* s, void* cuda_stream);
+
+/* ---- scene description: replaces PathTracer::AddObject / SceneBVH::AddObject
+ *      (cuSrc/path_tracer.cu:29-34, cuSrc/bvh.cu:22-29).  Return the primitive id (insertion index). */
+int pt_add_sphere(pt_scene* s, const float center[3], float radius);
+int pt_add_platform(pt_scene* s, float y_pos);
+int pt_add_cylinder(pt_scene* s, const float center[3], float radius, float height);
+/* replaces the by-hand fill of Object::material_ (include/object.h:26) */
+int pt_set_material(pt_scene* s, int prim, const pt_material* m);
+/* replaces SceneBVH::UpdateObject (cuSrc/bvh.cu:144-157); takes effect at the next pt_build */
+int pt_update_prim(pt_scene* s, int prim, const float center[3], float radius, float y_pos, float height);
+/* replaces PocaTextureUtils::AddTexByFile("textures\\sky.png") (cuSrc/path_tracer.cu:47,
+ * cuSrc/textures.cu:14-62) minus the OpenCV decode: the caller passes decoded RGBA8 rows */
+int pt_set_sky_rgba8(pt_scene* s, const uint8_t* rgba, int width, int height);
+/* replaces PathTracer::InitPipeline -> SceneBVH::BuildBVH (cuSrc/path_tracer.cu:308-314,
+ * cuSrc/bvh.cu:116-120): uploads the primitives and builds the LBVH on the device */
+int pt_build(pt_scene* s);
+
+/* ---- render: replaces the SamplePixel launches of PathTracer::PipelineLoop
+ *      (cuSrc/path_tracer.cu:124-175,276-279).  Traces samples [first_sample, first_sample+spp) of
+ *      every pixel and ADDS their radiance to the scene's accumulation buffer (fp32 sum, sample
+ *      order).  Returns after the device finished. */
+int pt_render_frame(pt_scene* s, const pt_camera* cam, int spp, int max_depth, uint64_t seed, uint32_t first_sample);
+/* same, but only enqueues the work on the scene's stream */
+int pt_render_frame_async(pt_scene* s, const pt_camera* cam, int spp, int max_depth, uint64_t seed, uint32_t first_sample);
+int pt_synchronize(pt_scene* s);
+/* zero the accumulation buffer (the reference's only reset is MotionalCamera::Refresh,
+ * cuSrc/motional_camera.cu:43-45 + path_tracer.cu:250) */
+int pt_reset_accum(pt_scene* s);
+/* mean radiance per pixel: rgba[4*(y*width+x)+{0,1,2}] = sum/samples, [3] = samples accumulated.
+ * nfloats must be 4*width*height. */
+int pt_read_accum(pt_scene* s, float* rgba, size_t nfloats);
+/* the device-resident SUM buffer (float4 per pixel: r,g,b,samples) for the caller's own reduction
+ * across GPUs (torch.distributed / NCCL); valid until the frame size changes or the scene dies */
+int pt_accum_device_ptr(pt_scene* s, float** dptr, size_t* nfloats);
+int pt_get_stats(pt_scene* s, pt_stats* out);
+
+/* ---- display pipeline: replaces Denoising + Mix + the D2H copy of PipelineLoop
+ *      (cuSrc/path_tracer.cu:177-254,285-304).  See pt_dispatch_ray in DESIGN.md. */
+int pt_dispatch_ray(pt_scene* s, const pt_camera* cam, int max_depth, uint64_t seed, uint32_t sample_idx,
+                    uint8_t* bgra_out, size_t nbytes);
+
+/* ---- textures: replaces PocaTextureUtils::{AddTexByFile,DestroyTexture} for material textures */
+int pt_texture_create_rgba8(pt_scene* s, const uint8_t* rgba, int width, int height, uint64_t* handle);
+int pt_texture_destroy(pt_scene* s, uint64_t handle);
+
+/* ---- parity entry points: the SAME device code as the render path, on caller-supplied batches.
+ *      rays8: n x (ox oy oz dx dy dz tmin tmax).  Outputs may be NULL. */
+/* closest hit (SceneBVH::TraceRay + Object::IntersectionTest, bvh.cu:167-205, object.cu:10-128) */
+int pt_trace_rays(pt_scene* s, int n, const float* rays8, int32_t* prim, float* t, float* normal3, float* hitpos3);
+/* Material::EvalAttenuationAndCreateRay with the uniforms given instead of drawn (material.cu:145-163) */
+int pt_shade_batch(pt_scene* s, int n, const pt_material* mats, int n_mats, const int32_t* mat_idx,
+                   const float* pos3, const float* normal3, const float* in_dir3, const float* u3,
+                   float* bounce3, float* atten3, float* radiance3, int32_t* n_draws);
+/* MotionalCamera::RayGen with the uniforms given (motional_camera.cu:202-213); xy: n x (x,y) */
+int pt_raygen_batch(pt_scene* s, const pt_camera* cam, int n, const int32_t* xy, const float* u3, float* rays8);
+/* Miss + sky texture (path_tracer.cu:117-122, textures.cu:68-71) */
+int pt_sky_lookup(pt_scene* s, int n, const float* dir3, float* rgb3);
+/* the uniforms the render path draws for (pixel, sample, slot): u4 = n x 4 */
+int pt_philox_uniforms(pt_scene* s, int n, uint64_t seed, const uint32_t* pixel_sample_slot3, float* u4);
+/* MotionalCamera::GetCopy basis (host math): out19 = u v w top_left horizontal vertical dist_to_focus */
+int pt_camera_basis(const pt_camera* cam, float out19[19]);
+
+const char* pt_last_error(void);
+const char* pt_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PT_API_H */

@@ -13,7 +13,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_ref", "libpt_ref_host.so")
+LIB_PATH = os.path.join(_HERE, "_ref", "libpt_ref_host.so")      # the reference's own code, host build
+PORT_LIB_PATH = os.path.join(_HERE, "libpt_oracle.so")            # the restatement (oracle/pt_oracle.cpp)
 
 
 class RefMaterial(C.Structure):
@@ -37,6 +38,22 @@ def available() -> bool:
     return os.path.exists(LIB_PATH)
 
 
+def port_available() -> bool:
+    return os.path.exists(PORT_LIB_PATH)
+
+
+class _Prefixed:
+    """Resolves `lib.ref_xyz` to `<prefix>xyz` so one wrapper drives both oracle libraries."""
+
+    def __init__(self, lib, prefix):
+        self._lib, self._prefix = lib, prefix
+
+    def __getattr__(self, name):
+        if name.startswith("ref_"):
+            name = self._prefix + name[4:]
+        return getattr(self._lib, name)
+
+
 def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t))
 
@@ -44,8 +61,9 @@ def _p(a, t):
 class RefHost:
     """One process-wide scene (the reference keeps its BVH in file-static state, bvh.cu:16-20)."""
 
-    def __init__(self, path: str = LIB_PATH):
-        self.lib = C.CDLL(path)
+    def __init__(self, path: str = LIB_PATH, prefix: str = "ref_"):
+        self.kind = "reference" if prefix == "ref_" else "port"
+        self.lib = _Prefixed(C.CDLL(path), prefix)
         L = self.lib
         L.ref_add_object.restype = C.c_int
         L.ref_add_object.argtypes = [C.c_int, C.POINTER(C.c_float), C.c_float, C.c_float, C.c_float,
@@ -152,3 +170,17 @@ class RefHost:
 
     def max_threads(self) -> int:
         return int(self.lib.ref_max_threads())
+
+
+class PortOracle(RefHost):
+    """The CPU restatement oracle/pt_oracle.cpp (same entry points, prefix orc_)."""
+
+    def __init__(self, path: str = PORT_LIB_PATH):
+        super().__init__(path, "orc_")
+
+
+def best_oracle():
+    """The reference's own code when its host build is present, else the restatement."""
+    if available():
+        return RefHost()
+    return PortOracle()
