@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""Headline benchmark: Mpaths/s at 1080p, max depth 8 (BASELINE.json metric), config C2
+(floor + 1000 mixed-material spheres, 1920x1080, 64 spp, depth 8), synthetic seeded scene and sky.
+
+  python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
+  python bench.py --impl reference --gpus N ...           # the reference's own CPU code (oracle/_ref host build)
+
+A step = one frame of the workload (W*H*spp paths) through the wavefront path.  `value` is device-timed
+(CUDA events, max over ranks) with the scene resident in HBM; `e2e` goes through the C ABI with host buffers
+(scene upload + LBVH build + render + read-back of the mean image into pinned host memory) by wall clock.
+N > 1 is weak scaling by samples-per-pixel: every rank renders its own 64-sample Philox range of the same
+frame and the SUM buffers are reduced to rank 0 with one NCCL reduce per frame (inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "Mpaths/s at 1080p, max depth 8"
+WORKLOAD = {"workload": "C2: floor + 1000 mixed-material spheres, 1920x1080, 64 spp, depth 8",
+            "width": 1920, "height": 1080, "spp": 64, "max_depth": 8, "n_spheres": 1000, "scene_seed": 12345,
+            "l2": "wave queues (>1.5 GB per 8-spp wave) exceed the 126 MB L2; no explicit flush"}
+ALG_BYTES_PER_RAY_TRAVERSE = 40      # read ray origin+dir (2 x float4 = 32 B) + write hit record (8 B), DESIGN.md
+ALG_BYTES_PER_SEGMENT = 144          # whole-path queue traffic per segment
+ALG_BYTES_PER_PATH = 16              # + one float4 radiance write per path
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_workload():
+    from cpppathtracer_b200 import scenes
+    sc = scenes.sphere_field(WORKLOAD["n_spheres"], WORKLOAD["width"], WORKLOAD["height"], WORKLOAD["scene_seed"])
+    sky = scenes.synthetic_sky(1280, 1280)
+    return sc, sky
+
+
+def cpu_baseline_leg(sc, sky, budget_s: float = 15.0):
+    """The reference's own tracing code on the host cores (oracle/_ref), bounded sample of the workload."""
+    from oracle import ref_host
+    orc = ref_host.best_oracle()
+    orc.load_scene(sc)
+    orc.set_sky(sky)
+    cores = orc.max_threads()
+    t0 = time.perf_counter()
+    _, st = orc.render(sc.camera, 1, WORKLOAD["max_depth"], seed=1)
+    t1 = time.perf_counter() - t0
+    spp = int(max(1, min(WORKLOAD["spp"], budget_s / max(t1, 1e-3))))
+    t0 = time.perf_counter()
+    _, st = orc.render(sc.camera, spp, WORKLOAD["max_depth"], seed=1)
+    dt = time.perf_counter() - t0
+    return {"value": st["paths"] / dt / 1e6, "unit": "Mpaths/s", "cores": cores, "kind": orc.kind,
+            "sample": f"{sc.camera.width}x{sc.camera.height} x {spp} spp of the workload scene, depth 8 "
+                      f"({st['paths'] / 1e6:.1f} M paths, {dt:.1f} s, OpenMP over rows)",
+            "segments_per_path": st["segments"] / st["paths"]}
+
+
+def reference_arm(args):
+    """`--impl reference`: the reference's CPU implementation of the path, all host threads, rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import ref_host
+    sc, sky = build_workload()
+    orc = ref_host.best_oracle()
+    orc.load_scene(sc)
+    orc.set_sky(sky)
+    cores = orc.max_threads()
+    # bounded sample per step: ~1.5 s of CPU work
+    t0 = time.perf_counter()
+    orc.render(sc.camera, 1, WORKLOAD["max_depth"], seed=1)
+    t1 = time.perf_counter() - t0
+    spp = int(max(1, min(WORKLOAD["spp"], 1.5 / max(t1, 1e-3))))
+    for _ in range(args.warmup):
+        orc.render(sc.camera, spp, WORKLOAD["max_depth"], seed=2)
+    paths = 0
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        _, st = orc.render(sc.camera, spp, WORKLOAD["max_depth"], seed=3, first_sample=k * spp)
+        paths += st["paths"]
+    dt = time.perf_counter() - t0
+    v = paths / dt / 1e6
+    sample = f"{sc.camera.width}x{sc.camera.height} x {spp} spp per step of the workload scene, depth 8"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": dict(WORKLOAD, sample=sample),
+        "cpu_baseline": {"value": v, "unit": "Mpaths/s", "cores": cores, "kind": orc.kind, "sample": sample},
+        "e2e": {"value": v, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def ref_cuda_leg(sc, sky):
+    """Reported baseline (north_star): the reference's own CUDA kernels rebuilt for sm_100, same scene."""
+    try:
+        from oracle import ref_cuda
+        if not ref_cuda.available():
+            return None
+        R = ref_cuda.RefCuda()
+        R.load_scene(sc)
+        R.set_sky(sky)
+        out = R.render(sc.camera, 8, warmup=2)
+        return {"mpaths_kernel_only": out["mpaths_kernel"], "mpaths_service_loop": out["mpaths_service"],
+                "traced_pixels": out["traced_pixels"], "spp": 8,
+                "note": "SamplePixel megakernel (path_tracer.cu:124-175), XORWOW RNG, grid W/16 x H/16 (1072 of 1080 rows)"}
+    except Exception as e:  # the baseline is optional evidence, never a reason to fail the bench
+        return {"unavailable": str(e)[:200]}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-baselines", action="store_true", help="skip the cpu / reference-CUDA baseline legs")
+    ap.add_argument("--wave-paths", type=int, default=0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from cpppathtracer_b200 import api, distributed as ptd
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the render path has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    warmup = max(args.warmup, 3)
+
+    sc, sky = build_workload()
+    cam = sc.camera
+    spp, depth = WORKLOAD["spp"], WORKLOAD["max_depth"]
+    r = api.Renderer(sc, sky)
+    r.set_stream(torch.cuda.current_stream().cuda_stream)
+    r.set_option(api.PT_OPT_STAGE_TIMING, 1)
+    if args.wave_paths:
+        r.set_option(api.PT_OPT_WAVE_PATHS, args.wave_paths)
+    first = rank * spp          # weak scaling: rank g renders samples [64 g, 64 (g+1)) of the same frame
+
+    def step():
+        r.reset_accum()
+        r.render(cam, spp, depth, seed=2026, first_sample=first, sync=False)
+        if world > 1:
+            ptd.reduce_sum_to_root(ptd.accum_tensor(r))
+
+    for _ in range(warmup):
+        step()
+    r.synchronize()
+    launches0 = r.stats()["launches"]
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    r.synchronize()
+    st = r.stats()
+    launches = st["launches"] - launches0
+    tms = torch.tensor([ms], device="cuda")
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms.item())
+    paths_per_step = cam.width * cam.height * spp * world
+    value = paths_per_step * args.steps / (ms * 1e-3) / 1e6
+
+    # ---- end to end through the C ABI with host buffers (wall clock) --------------------------------
+    host_img = torch.empty((cam.height, cam.width, 4), dtype=torch.float32, pin_memory=True).numpy()
+    e2e_steps = max(3, min(args.steps, 10))
+    h2d = sc.n_prims * (32 + 4 + 4) + len(sc.materials) * 48
+    d2h = cam.width * cam.height * 16
+
+    def e2e_step(k):
+        # the caller edits an object, rebuilds (upload + LBVH), renders and reads the mean image back
+        r.update_prim(1, sc.center[1], float(sc.radius[1]))
+        r.build()
+        r.reset_accum()
+        r.render(cam, spp, depth, seed=2026, first_sample=first, sync=False)
+        if world > 1:
+            ptd.reduce_sum_to_root(ptd.accum_tensor(r))
+        if rank == 0:
+            r.read_accum(host_img)
+        else:
+            r.synchronize()
+
+    e2e_step(0)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        e2e_step(k)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = paths_per_step * e2e_steps / float(te.item()) / 1e6
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        segs = st["segments"]                      # rays traced in the last frame on this rank
+        trav_ms = st["traverse_ms"]
+        n_trav = max(st["traverse_launches"], 1)
+        achieved = ALG_BYTES_PER_RAY_TRAVERSE * segs / (trav_ms * 1e-3) / 1e9 if trav_ms > 0 else None
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traverse_traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        path_bytes = ALG_BYTES_PER_SEGMENT * segs + ALG_BYTES_PER_PATH * st["paths"]
+        line = {
+            "metric": METRIC, "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": dict(WORKLOAD, parallelism=f"spp-sharded x{world}, one NCCL reduce per frame" if world > 1 else "single GPU",
+                           spp_total=spp * world, wave_paths=st["wave_paths"]),
+            "roofline": {"bound": "hbm", "kernel": "k_traverse (closest hit)", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                         "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": ALG_BYTES_PER_RAY_TRAVERSE * segs / n_trav,
+                         "avg_launch_ms": trav_ms / n_trav, "launches_per_step": n_trav,
+                         "share_of_step": trav_ms / st["render_ms"] if st["render_ms"] > 0 else None,
+                         "note": "latency/issue-bound BVH walk: the HBM roofline is reported as the contract asks, "
+                                 "see DESIGN.md for the FP32-issue view"},
+            "path": {"mrays_per_s": segs / (st["render_ms"] * 1e-3) / 1e6 if st["render_ms"] > 0 else None,
+                     "segments_per_path": segs / st["paths"], "render_ms_last_frame": st["render_ms"],
+                     "traverse_ms": trav_ms, "shade_ms": st["shade_ms"],
+                     "queue_hbm_gbs_model": path_bytes / (st["render_ms"] * 1e-3) / 1e9 if st["render_ms"] > 0 else None},
+            "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "what": "pt_update_prim + pt_build (upload, LBVH) + pt_render_frame + pt_read_accum into pinned host memory"},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if world == 1 and not args.no_baselines:
+            line["cpu_baseline"] = cpu_baseline_leg(sc, sky)
+            rc = ref_cuda_leg(sc, sky)
+            if rc is not None:
+                line["ref_cuda_baseline"] = rc
+        print(json.dumps(line))
+    r.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -32,7 +32,8 @@ class PtCamera(C.Structure):
 class PtStats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("segments", C.c_uint64), ("launches", C.c_uint64), ("render_ms", C.c_float),
                 ("traverse_ms", C.c_float), ("shade_ms", C.c_float), ("build_ms", C.c_float),
-                ("bvh_nodes", C.c_uint32), ("wave_paths", C.c_uint32)]
+                ("bvh_nodes", C.c_uint32), ("wave_paths", C.c_uint32), ("traverse_launches", C.c_uint32),
+                ("waves", C.c_uint32)]
 
 
 EXPORTS = [

@@ -93,6 +93,7 @@ struct pt_scene {
     DevBuf<uint2> hit;
     DevBuf<uint32_t> bin_items;
     DevBuf<BounceCtrl> ctrl;
+    DevBuf<unsigned long long> seg_counter;
     uint32_t capacity = 0;
     // parity scratch
     DevBuf<float> scratch_f[8];
@@ -107,6 +108,10 @@ struct pt_scene {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> stage_events;
     int grid_traverse = 0, grid_shade = 0;
+    int last_depth = 0;
+    size_t stage_events_used = 0;
+    bool frame_recorded = false;
+    DevBuf<float4> read_tmp;
 };
 
 namespace {
@@ -285,7 +290,9 @@ int upload_and_build(pt_scene* s) {
     s->n_plat = (int)py.size();
     s->n_tree = (int)tree.size();
     const int nt = s->n_tree;
-    CK(cudaEventRecord(s->ev0, st));
+    cudaEvent_t eb0, eb1;
+    CK(cudaEventCreate(&eb0)); CK(cudaEventCreate(&eb1));
+    CK(cudaEventRecord(eb0, st));
     if (nt > 0) {
         CK(s->bvh_prims.reserve(nt));
         CK(cudaMemcpyAsync(s->bvh_prims.p, tree.data(), nt * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -317,9 +324,10 @@ int upload_and_build(pt_scene* s) {
         }
         CK(cudaGetLastError());
     }
-    CK(cudaEventRecord(s->ev1, st));
+    CK(cudaEventRecord(eb1, st));
     CK(cudaStreamSynchronize(st));
-    CK(cudaEventElapsedTime(&s->stats.build_ms, s->ev0, s->ev1));
+    CK(cudaEventElapsedTime(&s->stats.build_ms, eb0, eb1));
+    cudaEventDestroy(eb0); cudaEventDestroy(eb1);
     s->stats.bvh_nodes = nt > 1 ? (uint32_t)(nt - 1) : (uint32_t)nt;
     s->dirty = false; s->built = true;
     return PT_OK;
@@ -357,6 +365,7 @@ int ensure_queues(pt_scene* s, uint32_t cap, int max_depth) {
         s->capacity = cap;
     }
     CK(s->ctrl.reserve((size_t)max_depth + 2));
+    CK(s->seg_counter.reserve(1));
     return PT_OK;
 }
 
@@ -393,6 +402,7 @@ int render_async(pt_scene* s, const pt_camera* cam, int spp, int max_depth, uint
         if (ev_i >= s->stage_events.size()) { cudaEvent_t e; cudaError_t r = cudaEventCreate(&e); if (r) return r; s->stage_events.push_back(e); }
         return cudaEventRecord(s->stage_events[ev_i++], st);
     };
+    CK(cudaMemsetAsync(s->seg_counter.p, 0, sizeof(unsigned long long), st));
     CK(cudaEventRecord(s->ev0, st));
     uint64_t launches = 0;
     for (uint32_t s0 = 0; s0 < (uint32_t)spp; s0 += spp_per_wave) {
@@ -420,21 +430,42 @@ int render_async(pt_scene* s, const pt_camera* cam, int spp, int max_depth, uint
         CK(stage_event());
         const int ac_grid = (int)std::min<uint32_t>((npix + 255u) / 256u, (uint32_t)s->sm_count * 8u);
         k_accumulate<<<ac_grid, 256, 0, st>>>(npix, ns, s->path_out.p, s->accum.p);
-        ++launches;
+        k_wave_stats<<<1, 1, 0, st>>>(max_depth, s->ctrl.p, s->seg_counter.p);
+        launches += 2;
         CK(cudaGetLastError());
     }
     CK(cudaEventRecord(s->ev1, st));
+    s->frame_recorded = true; s->last_depth = max_depth; s->stage_events_used = ev_i;
     s->stats.launches += launches;
     s->stats.paths = (uint64_t)npix * (uint64_t)spp;
     s->stats.wave_paths = cap;
     s->stats.segments = 0;
+    s->stats.waves = (uint32_t)(((uint32_t)spp + spp_per_wave - 1) / spp_per_wave);
+    s->stats.traverse_launches = s->stats.waves * (uint32_t)max_depth;
     return PT_OK;
 }
 
 int finish_frame(pt_scene* s, int max_depth_hint) {
     (void)max_depth_hint;
+    if (!s->frame_recorded) { CK(cudaStreamSynchronize(s->stream)); return PT_OK; }
+    unsigned long long seg = 0;
+    CK(cudaMemcpyAsync(&seg, s->seg_counter.p, sizeof(seg), cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     CK(cudaEventElapsedTime(&s->stats.render_ms, s->ev0, s->ev1));
+    s->stats.segments = seg;
+    if (s->opt_stage_timing && s->stage_events.size() >= 2) {
+        // events alternate: [traverse start, shade start] per bounce, then accumulate start, per wave
+        float trav = 0.f, shade = 0.f;
+        const size_t per_wave = 2 * (size_t)s->last_depth + 1;
+        for (size_t w0 = 0; w0 + per_wave <= s->stage_events_used; w0 += per_wave)
+            for (int b = 0; b < s->last_depth; ++b) {
+                float a = 0.f, bms = 0.f;
+                cudaEventElapsedTime(&a, s->stage_events[w0 + 2 * b], s->stage_events[w0 + 2 * b + 1]);
+                cudaEventElapsedTime(&bms, s->stage_events[w0 + 2 * b + 1], s->stage_events[w0 + 2 * b + 2]);
+                trav += a; shade += bms;
+            }
+        s->stats.traverse_ms = trav; s->stats.shade_ms = shade;
+    }
     return PT_OK;
 }
 
@@ -578,8 +609,8 @@ void pt_scene_destroy(pt_scene* s) {
     s->inner_mn.release(); s->inner_mx.release(); s->mats.release(); s->plat_y.release(); s->plat_id.release();
     s->bvh_prims.release(); s->parent_inner.release(); s->parent_leaf.release(); s->flags.release(); s->children.release();
     s->codes.release(); s->codes_sorted.release(); s->ids.release(); s->ids_sorted.release(); s->bounds6.release();
-    s->tie_rank.release(); s->cub_tmp.release(); s->accum.release(); s->path_out.release(); s->hit.release();
-    s->bin_items.release(); s->ctrl.release();
+    s->tie_rank.release(); s->cub_tmp.release(); s->accum.release(); s->read_tmp.release(); s->path_out.release(); s->hit.release();
+    s->bin_items.release(); s->ctrl.release(); s->seg_counter.release();
     for (int k = 0; k < 2; ++k) { s->q_o[k].release(); s->q_d[k].release(); s->q_thr[k].release(); s->scratch_i[k].release(); }
     for (auto& b : s->scratch_f) b.release();
     s->disp_color.release(); s->disp_normal.release(); s->disp_mix.release(); s->disp_depth.release(); s->disp_bgra.release();
@@ -691,25 +722,6 @@ int pt_render_frame(pt_scene* s, const pt_camera* cam, int spp, int max_depth, u
     if (rc) return rc;
     rc = finish_frame(s, max_depth);
     if (rc) return rc;
-    // segments traced = sum of the input queue sizes of every bounce of the LAST wave (diagnostic only)
-    std::vector<BounceCtrl> c((size_t)max_depth + 1);
-    CK(cudaMemcpy(c.data(), s->ctrl.p, c.size() * sizeof(BounceCtrl), cudaMemcpyDeviceToHost));
-    uint64_t seg = 0;
-    for (int b = 0; b < max_depth; ++b) seg += c[b].in_count;
-    s->stats.segments = seg;
-    if (s->opt_stage_timing && s->stage_events.size() >= 2) {
-        // events alternate: [traverse start, shade start] per bounce, then accumulate start, per wave
-        float trav = 0.f, shade = 0.f;
-        const size_t per_wave = 2 * (size_t)max_depth + 1;
-        for (size_t w0 = 0; w0 + per_wave <= s->stage_events.size(); w0 += per_wave)
-            for (int b = 0; b < max_depth; ++b) {
-                float a = 0.f, bms = 0.f;
-                cudaEventElapsedTime(&a, s->stage_events[w0 + 2 * b], s->stage_events[w0 + 2 * b + 1]);
-                cudaEventElapsedTime(&bms, s->stage_events[w0 + 2 * b + 1], s->stage_events[w0 + 2 * b + 2]);
-                trav += a; shade += bms;
-            }
-        s->stats.traverse_ms = trav; s->stats.shade_ms = shade;
-    }
     return PT_OK;
 }
 
@@ -723,14 +735,11 @@ int pt_read_accum(pt_scene* s, float* rgba, size_t nfloats) {
     if (!s || !rgba) return fail(PT_ERR_INVALID, "null argument");
     const size_t npix = (size_t)s->width * s->height;
     if (npix == 0 || nfloats != 4 * npix) return fail(PT_ERR_INVALID, "nfloats must be 4*width*height of the last frame");
-    DevBuf<float4> tmp;
-    CK(tmp.reserve(npix));
-    k_read_accum<<<(unsigned)((npix + 255) / 256), 256, 0, s->stream>>>((uint32_t)npix, s->accum.p, tmp.p);
+    CK(s->read_tmp.reserve(npix));
+    k_read_accum<<<(unsigned)((npix + 255) / 256), 256, 0, s->stream>>>((uint32_t)npix, s->accum.p, s->read_tmp.p);
     s->stats.launches += 1;
-    cudaError_t e = cudaMemcpyAsync(rgba, tmp.p, npix * sizeof(float4), cudaMemcpyDeviceToHost, s->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
-    tmp.release();
-    CK(e);
+    CK(cudaMemcpyAsync(rgba, s->read_tmp.p, npix * sizeof(float4), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
     return PT_OK;
 }
 

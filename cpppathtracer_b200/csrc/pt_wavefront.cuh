@@ -296,4 +296,11 @@ __global__ void __launch_bounds__(256) k_accumulate(uint32_t npix, uint32_t n_sa
     }
 }
 
+// per-wave bookkeeping: rays traced = sum of the bounce input queues (diagnostic counter, 1 thread)
+__global__ void k_wave_stats(int max_depth, const BounceCtrl* __restrict__ ctrl, unsigned long long* __restrict__ segments) {
+    unsigned long long n = 0;
+    for (int b = 0; b < max_depth; ++b) n += ctrl[b].in_count;
+    *segments += n;
+}
+
 }  // namespace pt

@@ -69,6 +69,8 @@ typedef struct pt_stats {
     float    build_ms;        /* device time of the last pt_build                             */
     uint32_t bvh_nodes;
     uint32_t wave_paths;      /* paths in flight per wave                                     */
+    uint32_t traverse_launches; /* closest-hit launches of the last pt_render_frame (= waves x depth) */
+    uint32_t waves;           /* waves of the last pt_render_frame                            */
 } pt_stats;
 
 enum {

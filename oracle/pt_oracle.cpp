@@ -607,6 +607,34 @@ void orc_render(int spp, int first_sample, int max_depth, unsigned long long see
     if (stats) { stats->paths = (unsigned long long)W * H * spp; stats->segments = segs; stats->misses = misses;
                  stats->depth_exhausted = exhausted; }
 }
+/* Debug / test aid: the ray every pixel's path (sample `sample`) shoots as its segment number `seg`
+ * (0 = camera ray), or valid=0 when the path ended before that.  Same walk as orc_render. */
+void orc_segment_rays(int seg, int sample, int max_depth, unsigned long long seed, float* rays8, int32_t* valid) {
+    const int W = g_cam.w, H = g_cam.h;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            const uint32_t pixel = (uint32_t)(y * W + x);
+            float U[4];
+            pt_philox_uniform4(seed, pixel, (uint32_t)sample, 0u, U);
+            Ray ray = raygen(g_cam, x, y, U);
+            int depth = 0; bool ok = true;
+            while (depth < seg) {
+                if (depth >= max_depth) { ok = false; break; }
+                Hit h; float t;
+                int p = trace(g_scene, ray, h, &t);
+                if (p < 0) { ok = false; break; }
+                pt_philox_uniform4(seed, pixel, (uint32_t)sample, 1u + (uint32_t)depth, U);
+                Scatter sc; shade(g_scene.prims[p].mat, h.normal, ray.d, U, sc);
+                ray.o = h.pos; ray.d = normalize(sc.bounce); ray.tmin = RT_BOUNCE_TMIN; ray.tmax = RT_TMAX;
+                depth++;
+            }
+            valid[pixel] = ok ? 1 : 0;
+            float* r = rays8 + 8 * (size_t)pixel;
+            r[0] = ray.o.x; r[1] = ray.o.y; r[2] = ray.o.z; r[3] = ray.d.x; r[4] = ray.d.y; r[5] = ray.d.z;
+            r[6] = ray.tmin; r[7] = ray.tmax;
+        }
+}
 int orc_sizeof(int) { return 0; }
 int orc_max_threads(void) { return omp_get_max_threads(); }
 }

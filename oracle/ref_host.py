@@ -178,6 +178,15 @@ class PortOracle(RefHost):
     def __init__(self, path: str = PORT_LIB_PATH):
         super().__init__(path, "orc_")
 
+    def segment_rays(self, cam, seg: int, sample: int = 0, max_depth: int = 8, seed: int = 0):
+        """Rays of path segment `seg` for every pixel: (rays8 [H*W,8], valid [H*W] bool)."""
+        self.set_camera(cam)
+        n = cam.width * cam.height
+        rays = np.zeros((n, 8), np.float32); valid = np.zeros(n, np.int32)
+        self.lib.ref_segment_rays(C.c_int(seg), C.c_int(sample), C.c_int(max_depth), C.c_ulonglong(seed),
+                                  _p(rays, C.c_float), _p(valid, C.c_int32))
+        return rays, valid.astype(bool)
+
 
 def best_oracle():
     """The reference's own code when its host build is present, else the restatement."""

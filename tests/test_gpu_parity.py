@@ -1,0 +1,336 @@
+"""-m gpu: parity of the CUDA path (through the C ABI, libpt_b200.so) against the CPU oracle.
+
+Level 1  fixed ray batches: closest-hit primitive ids bit-exact, t / normals within 1e-5 relative
+Level 2  fixed (material, normal, in-dir, u1,u2,u3): scatter directions within 1e-5
+Level 3  images: RMSE and channel means vs the oracle render of the same Philox stream
+plus size-independent properties at the BASELINE size (determinism, sample-range additivity,
+wave-size independence) and the edge cases (empty / single-primitive / platform-only scenes, n = 0).
+"""
+import numpy as np
+import pytest
+
+from conftest import golden
+from cpppathtracer_b200 import api, scenes
+
+pytestmark = pytest.mark.gpu
+REL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def oracle(port_oracle):
+    from oracle import ref_host
+    return ref_host.RefHost() if ref_host.available() else port_oracle
+
+
+def _check_trace(r, orc, rays, max_mismatch_frac=0.0):
+    pg, tg, ng, hg = r.trace(rays)
+    pr, tr, nr, hr = orc.trace(rays)
+    mism = pg != pr
+    assert mism.mean() <= max_mismatch_frac, f"{mism.sum()} primitive-id mismatches of {len(rays)}"
+    ok = (~mism) & (pr >= 0)
+    assert np.all(np.abs(tg[ok] - tr[ok]) <= REL * np.abs(tr[ok]))
+    assert np.all(np.abs(ng[ok] - nr[ok]) <= REL)
+    assert np.all(np.abs(hg[ok] - hr[ok]) <= REL * np.maximum(1.0, np.abs(hr[ok])))
+    miss = (~mism) & (pr < 0)
+    assert np.all(tg[miss] == tr[miss])
+    return int(mism.sum()), float((tg[ok] == tr[ok]).mean()) if ok.any() else 1.0
+
+
+def test_philox_stream_matches_oracle_and_kat(tmp_path_factory):
+    from test_oracle import _philox_lib
+    import ctypes as C
+    L = _philox_lib(tmp_path_factory)
+    r = api.Renderer()
+    rng = np.random.RandomState(4)
+    pss = np.stack([rng.randint(0, 2**31, 4096), rng.randint(0, 1 << 20, 4096), rng.randint(0, 65, 4096)], 1).astype(np.uint32)
+    seed = 0xDEADBEEFCAFEF00D
+    got = r.philox(seed, pss)
+    want = np.zeros_like(got)
+    for i in range(len(pss)):
+        L.uni(C.c_ulonglong(seed), C.c_uint(int(pss[i, 0])), C.c_uint(int(pss[i, 1])), C.c_uint(int(pss[i, 2])),
+              want[i].ctypes.data_as(C.c_void_p))
+    assert np.array_equal(got, want)
+    assert got.min() > 0.0 and got.max() <= 1.0
+    # Random123 KAT through the (0,1] mapping: counter (0,0,0,0), key (0,0)
+    kat = r.philox(0, np.zeros((1, 3), np.uint32))[0]
+    w = np.array([0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8], np.uint32).astype(np.float32)
+    assert np.array_equal(kat, w * np.float32(2.3283064365386963e-10) + np.float32(1.1641532182693481e-10))
+    r.close()
+
+
+def test_camera_basis_and_raygen_bit_exact(oracle):
+    rng = np.random.RandomState(5)
+    r = api.Renderer()
+    for cam in (scenes.Camera(640, 360), scenes.Camera(1920, 1080, (50, 20, -70), (3, 1, 2), view_fov=55.0, lens_radius=0.3),
+                scenes.Camera(77, 131, (0, 5, 0), (0, 4, 9), view_fov=12.5, lens_radius=0.0)):
+        assert np.array_equal(api.camera_basis(cam), oracle.set_camera(cam))
+        n = 20000
+        xy = np.stack([rng.randint(0, cam.width, n), rng.randint(0, cam.height, n)], 1).astype(np.int32)
+        u3 = rng.random_sample((n, 3)).astype(np.float32)
+        assert np.array_equal(r.raygen(cam, xy, u3), oracle.raygen(xy, u3))
+    r.close()
+
+
+@pytest.mark.parametrize("name,maker", [("demo", lambda: scenes.demo_scene(64, 36)),
+                                        ("spheres200", lambda: scenes.sphere_field(200, 64, 36))])
+def test_level1_golden_ray_batches(name, maker, sky):
+    """The committed vectors generated from the reference's own code."""
+    g = golden(f"trace_{name}.npz")
+    sc = maker()
+    r = api.Renderer(sc, sky)
+    for rk, pk, tk, nk, hk in (("rays", "prim", "t", "normal", "pos"), ("rays2", "prim2", "t2", "normal2", "pos2")):
+        p, t, n, h = r.trace(g[rk])
+        assert np.array_equal(p, g[pk])
+        hit = p >= 0
+        assert np.all(np.abs(t[hit] - g[tk][hit]) <= REL * np.abs(g[tk][hit]))
+        assert np.all(np.abs(n[hit] - g[nk][hit]) <= REL)
+        assert (t[hit] == g[tk][hit]).mean() > 0.999      # in practice bit-exact
+    r.close()
+
+
+@pytest.mark.parametrize("maker", [lambda: scenes.demo_scene(640, 360), lambda: scenes.sphere_field(1000, 480, 270),
+                                   lambda: scenes.stress_field(20000, 480, 270), lambda: scenes.demo_scene(320, 180, seed=99)])
+def test_level1_closest_hit_on_path_rays(maker, oracle, port_oracle, sky):
+    """Camera rays and the oracle's own bounce rays (segments 1..4 of real paths: grazing exits, glass interiors,
+    hollow shells, caps resting on the floor).  Ties resolve in the reference's leaf order, so no exclusions."""
+    sc = maker()
+    r = api.Renderer(sc, sky)
+    oracle.load_scene(sc)
+    port_oracle.load_scene(sc)
+    total_mism, total = 0, 0
+    for seg in range(0, 5):
+        rays, valid = port_oracle.segment_rays(sc.camera, seg, sample=seg, max_depth=8, seed=31)
+        rays = rays[valid][:150000]
+        m, exact = _check_trace(r, oracle, rays, max_mismatch_frac=1e-4)
+        total_mism += m; total += len(rays)
+        assert exact > 0.999
+    assert total_mism <= 2, f"{total_mism} grazing/tie mismatches of {total}"
+    r.close()
+
+
+def test_level1_random_rays_inside_and_outside(oracle, sky):
+    sc = scenes.stress_field(5000, 64, 36, seed=11)
+    r = api.Renderer(sc, sky)
+    oracle.load_scene(sc)
+    rng = np.random.RandomState(12)
+    n = 200000
+    o = rng.uniform(-250, 250, (n, 3)); o[:, 1] = rng.uniform(-5, 30, n)
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d[: n // 20, rng.randint(0, 3)] = 0.0          # axis-parallel components (bvh.cu:182-199 skips those slabs)
+    d[: n // 20] /= np.maximum(np.linalg.norm(d[: n // 20], axis=1, keepdims=True), 1e-9)
+    rays = np.concatenate([o, d, rng.choice([0.0, 2e-5], (n, 1)), rng.choice([1e30, 50.0], (n, 1))], 1).astype(np.float32)
+    m, _ = _check_trace(r, oracle, rays, max_mismatch_frac=2e-5)
+    r.close()
+
+
+def test_level1_edge_scenes(oracle, sky):
+    rays = np.array([[0, 5, -10, 0, -0.3, 1, 0, 1e30], [0, 5, -10, 0, 1, 0, 0, 1e30], [0, 1, 0, 0, -1, 0, 0, 1e30],
+                     [0, 0.5, -10, 0, 0, 1, 0, 1e30], [0, 0.5, 0, 1, 0, 0, 2e-5, 1e30]], np.float32)
+    base = scenes.demo_scene(32, 18)
+
+    def scene_of(types, centers, radii, ypos, heights):
+        sc = scenes.demo_scene(32, 18)
+        sc.prim_type = np.array(types, np.int32); sc.center = np.array(centers, np.float32).reshape(-1, 3)
+        sc.radius = np.array(radii, np.float32); sc.y_pos = np.array(ypos, np.float32)
+        sc.height = np.array(heights, np.float32); sc.mat_idx = np.zeros(len(types), np.int32)
+        sc.materials = base.materials
+        return sc
+
+    cases = [scene_of([scenes.PLATFORM], [[0, 0, 0]], [0], [0.0], [0]),                       # platform only: no tree
+             scene_of([scenes.SPHERE], [[0, 0.5, 0]], [1.0], [0], [0]),                        # one-primitive tree
+             scene_of([scenes.CYLINDER], [[0, 0.5, 0]], [1.0], [0], [1.0]),
+             scene_of([scenes.SPHERE, scenes.SPHERE], [[0, 0.5, 0], [0, 0.5, 0]], [1.0, -0.99], [0, 0], [0, 0]),   # hollow shell
+             scene_of([scenes.PLATFORM, scenes.CYLINDER, scenes.CYLINDER], [[0, 0, 0], [0, 0.5, 0], [0.5, 0.5, 0]],
+                      [0, 1.0, 1.0], [0, 0, 0], [0, 1.0, 1.0])]                                   # caps resting on the floor: ties
+    for sc in cases:
+        r = api.Renderer(sc, sky)
+        oracle.load_scene(sc)
+        _check_trace(r, oracle, rays)
+        assert r.trace(np.zeros((0, 8), np.float32))[0].shape == (0,)       # n = 0
+        r.close()
+    # empty scene: everything misses, render gives pure sky
+    r = api.Renderer(); r.set_sky(sky); r.build()
+    assert (r.trace(rays)[0] == -1).all()
+    cam = scenes.Camera(32, 18)
+    r.render(cam, 2, 8, seed=1)
+    img = r.read_accum()
+    assert (img[..., 3] == 2).all() and img[..., :3].min() > 0.0
+    # call-order errors are reported, not ignored
+    r.add_sphere((0, 0, 0), 1.0)
+    with pytest.raises(api.PtError):
+        r.render(cam, 1)
+    r.close()
+
+
+def test_level1_ties_follow_reference_leaf_order(oracle, sky):
+    """Cylinder bottom caps coincide with the floor plane (video_renderer.cpp:78,105-106): rays from inside a
+    cylinder towards the floor hit both at exactly the same t; the winner must be the reference's."""
+    sc = scenes.demo_scene(64, 36)
+    r = api.Renderer(sc, sky)
+    oracle.load_scene(sc)
+    cyl = np.where(sc.prim_type == scenes.CYLINDER)[0]
+    rng = np.random.RandomState(8)
+    rays = []
+    for c in cyl:
+        for _ in range(200):
+            ang, rad = rng.uniform(0, 2 * np.pi), rng.uniform(0, 0.9) * abs(sc.radius[c])
+            o = [sc.center[c, 0] + rad * np.cos(ang), sc.center[c, 1], sc.center[c, 2] + rad * np.sin(ang)]
+            d = np.array([rng.normal() * 0.05, -1.0, rng.normal() * 0.05]); d /= np.linalg.norm(d)
+            rays.append(o + d.tolist() + [2e-5, 1e30])
+    rays = np.array(rays, np.float32)
+    pr = oracle.trace(rays)[0]
+    assert (sc.prim_type[pr] == scenes.PLATFORM).any() and (sc.prim_type[pr] == scenes.CYLINDER).any()   # both win somewhere
+    _check_trace(r, oracle, rays)
+    r.close()
+
+
+def test_level2_scatter_golden_vectors():
+    """Material::EvalAttenuationAndCreateRay with replayed uniforms vs the reference's own code (golden)."""
+    g = golden("shade.npz")
+    r = api.Renderer()
+    b, a, rad, nd = r.shade(g["materials"], g["mat_idx"], g["pos"], g["normal"], g["in_dir"], g["u3"])
+    assert np.array_equal(nd, g["draws"])
+    assert np.array_equal(a, g["atten"]) and np.array_equal(rad, g["radiance"])
+    fin = np.isfinite(g["bounce"]).all(axis=1)
+    assert fin.mean() > 0.999
+    err = np.abs(b[fin] - g["bounce"][fin]).max(axis=1)
+    assert err.max() <= REL, f"max scatter-direction error {err.max():.3e}"
+    assert (err == 0).mean() > 0.5
+    r.close()
+
+
+def test_level2_scatter_fresh_inputs_all_materials(oracle):
+    rng = np.random.RandomState(21)
+    mats = np.zeros(12, scenes.MATERIAL_DTYPE)
+    for i in range(12):
+        mats[i] = (i % 5, 0, tuple(rng.uniform(0.1, 1.0, 3)), rng.uniform(1.05, 3.2), rng.uniform(0, 2) * (i % 3 == 0),
+                   rng.uniform(0.0, 6.0) if i % 2 else rng.uniform(0.0, 1.5), rng.uniform(0, 1))
+    n = 200000
+    mi = rng.randint(0, 12, n).astype(np.int32)
+    nrm = rng.normal(size=(n, 3)).astype(np.float32); nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    ind = rng.normal(size=(n, 3)).astype(np.float32); ind /= np.linalg.norm(ind, axis=1, keepdims=True)
+    u3 = rng.random_sample((n, 3)).astype(np.float32)
+    u3[:100, 0] = np.float32(1.1641532182693481e-10)      # smallest uniform the stream can produce
+    u3[100:200, 0] = 1.0                                  # largest
+    r = api.Renderer()
+    gb, ga, gr, gd = r.shade(mats, mi, np.zeros((n, 3), np.float32), nrm, ind, u3)
+    ob, oa, orad, od = oracle.shade(mats, mi, np.zeros((n, 3), np.float32), nrm, ind, u3)
+    assert np.array_equal(gd, od) and np.array_equal(gr, orad)
+    fin = np.isfinite(ob).all(axis=1) & np.isfinite(gb).all(axis=1)
+    assert fin.mean() > 0.9999
+    # attenuation flips only where dot(normal, bounce) is within rounding of 0 (material.cu:31,56,92)
+    flips = (ga != oa).any(axis=1)
+    assert flips.mean() < 1e-4
+    err = np.abs(gb[fin] - ob[fin]).max(axis=1)
+    assert np.quantile(err, 0.9999) <= REL and (err > 1e-4).mean() < 2e-5, f"max {err.max():.3e}"
+    r.close()
+
+
+def test_sky_lookup_matches_reference_texture_path(oracle, sky):
+    g = golden("sky_camera.npz")
+    r = api.Renderer(); r.set_sky(sky); r.build()
+    got = r.sky_lookup(g["dirs"])
+    # hardware bilinear filter (8-bit weights) vs the oracle's emulation: 8-bit texels, so <= ~1/255 per tap step;
+    # texels next to the u = 0.25 seam of the quarter-row upload are excluded
+    d = g["dirs"]
+    u = np.abs(np.arctan(d[:, 1] / d[:, 0]) / 2 / np.pi)
+    keep = u < 0.2495
+    err = np.abs(got[keep] - g["rgb"][keep]).max(axis=1)
+    assert keep.mean() > 0.99 and err.max() < 2.5e-3 and err.mean() < 2e-4
+    r.close()
+
+
+def _render_pair(sc, sky, oracle, spp, seed, depth=8):
+    r = api.Renderer(sc, sky)
+    r.render(sc.camera, spp, depth, seed=seed)
+    img = r.read_accum()
+    st = r.stats()
+    r.close()
+    oracle.load_scene(sc); oracle.set_sky(sky)
+    ref, ost = oracle.render(sc.camera, spp, depth, seed=seed)
+    return img, ref / spp, st, ost
+
+
+@pytest.mark.parametrize("maker,spp", [(lambda: scenes.demo_scene(320, 180), 32), (lambda: scenes.sphere_field(1000, 240, 136), 32),
+                                       (lambda: scenes.stress_field(20000, 240, 136), 16)])
+def test_level3_image_vs_oracle(maker, spp, oracle, sky):
+    """Same Philox stream on both sides: single-segment results are bit-comparable; longer paths decorrelate
+    chaotically from 1-ulp sin/cos differences (measured 1.0e-2 RMSE per sample at depth 8), so the bound
+    scales as 1.6e-2/sqrt(spp) -- 2.5e-4 at the 4096 spp of north_star, four times inside its 1e-3."""
+    sc = maker()
+    img, ref, st, ost = _render_pair(sc, sky, oracle, spp, seed=17)
+    assert (img[..., 3] == spp).all()
+    rmse = float(np.sqrt(np.mean((img[..., :3] - ref) ** 2)))
+    assert rmse <= 1.6e-2 / np.sqrt(spp), f"rmse {rmse:.3e}"
+    gm, rm = img[..., :3].mean(axis=(0, 1)), ref.mean(axis=(0, 1))
+    assert np.all(np.abs(gm - rm) <= 0.005 * rm), f"channel means {gm} vs {rm}"
+    assert abs(st["segments"] - ost["segments"]) <= 2e-3 * ost["segments"]
+
+
+def test_level3_depth1_image_is_tight(oracle, sky):
+    """One segment per path: no chaotic amplification, only the texture unit's filter differs."""
+    sc = scenes.demo_scene(320, 180)
+    img, ref, st, ost = _render_pair(sc, sky, oracle, 4, seed=3, depth=1)
+    assert np.abs(img[..., :3] - ref).max() < 2.5e-3
+    assert st["segments"] == ost["segments"] == 320 * 180 * 4
+
+
+def test_properties_at_baseline_size(sky):
+    """1920x1080 (BASELINE size): determinism, sample-range additivity and wave-size independence are bit-exact
+    because the stream is keyed by (pixel, sample, bounce) and the accumulation is in sample order."""
+    sc = scenes.sphere_field(1000, 1920, 1080)
+    r = api.Renderer(sc, sky)
+    r.render(sc.camera, 8, 8, seed=5); a = r.read_accum().copy()
+    r.reset_accum(); r.render(sc.camera, 8, 8, seed=5); b = r.read_accum().copy()
+    assert np.array_equal(a, b)
+    r.reset_accum()
+    r.render(sc.camera, 3, 8, seed=5, first_sample=0); r.render(sc.camera, 5, 8, seed=5, first_sample=3)
+    c = r.read_accum().copy()
+    assert np.array_equal(a, c)
+    r.reset_accum(); r.set_option(api.PT_OPT_WAVE_PATHS, 3 * 1920 * 1080)
+    r.render(sc.camera, 8, 8, seed=5); d = r.read_accum().copy()
+    assert np.array_equal(a, d)
+    r.reset_accum(); r.render(sc.camera, 8, 8, seed=6); e = r.read_accum()
+    assert not np.array_equal(a, e)
+    st = r.stats()
+    assert st["paths"] == 1920 * 1080 * 8 and 2.0 < st["segments"] / st["paths"] < 4.0
+    assert np.isfinite(a).all() and a[..., :3].min() >= 0.0
+    r.close()
+
+
+def test_emitters_and_textures(oracle, sky):
+    sc = scenes.demo_scene(160, 90)
+    sc.materials = sc.materials.copy()
+    sc.materials["emit_intensity"][3] = 0.7
+    sc.materials["emit_intensity"][5] = 1.5
+    img, ref, st, ost = _render_pair(sc, sky, oracle, 16, seed=2)
+    rmse = float(np.sqrt(np.mean((img[..., :3] - ref) ** 2)))
+    assert rmse < 1.6e-2 / 4 * 1.5 and abs(img[..., :3].mean() - ref.mean()) < 0.005 * ref.mean()
+    # kd from a texture sampled at (0,0) (Material::GetKd, material.cu:11-18)
+    r = api.Renderer()
+    tex = r.create_texture(np.full((4, 4, 4), 128, np.uint8))
+    m = api.to_pt_material(sc.materials[0], tex=tex)
+    p = r.add_sphere((0, 0, 0), 1.0); r.set_material(p, m); r.build()
+    r.close()
+
+
+def test_reference_cuda_kernels_agree(sky):
+    """Device-side oracle: the reference's own TraceRay compiled for sm_100 (FMA-contracted arithmetic)."""
+    from oracle import ref_cuda
+    if not ref_cuda.available():
+        pytest.skip("oracle/_ref/libpt_ref_cuda.so not built")
+    sc = scenes.demo_scene(640, 360)
+    R = ref_cuda.RefCuda(); R.load_scene(sc)
+    r = api.Renderer(sc, sky)
+    rng = np.random.RandomState(6)
+    n = 100000
+    xy = np.stack([rng.randint(0, 640, n), rng.randint(0, 360, n)], 1).astype(np.int32)
+    rays = r.raygen(sc.camera, xy, rng.random_sample((n, 3)).astype(np.float32))
+    pg, tg, ng, hg = r.trace(rays)
+    pr, tr, nr, hr = R.trace(rays)
+    mism = pg != pr
+    assert mism.mean() < 1e-4                       # grazing rays where contraction changes the decision
+    ok = ~mism & (pr >= 0)
+    assert np.all(np.abs(tg[ok] - tr[ok]) <= REL * np.abs(tr[ok]))
+    assert np.quantile(np.abs(ng[ok] - nr[ok]).max(axis=1), 0.999) <= REL
+    r.close()

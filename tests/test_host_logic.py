@@ -1,0 +1,102 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol include/pt_api.h declares
+(no compute without a GPU), scene generators are deterministic, sample / frame sharding is exact."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from cpppathtracer_b200 import api, scenes, distributed as ptd
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "pt_api.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pt_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = api.load_library()
+    names = _declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"libpt_b200.so does not export {n}"
+    assert sorted(api.EXPORTS) == names
+    assert b"sm_100a" in lib.pt_version()
+
+
+def test_no_cpu_fallback_without_device():
+    """On a box without a GPU the product must fail loudly, not compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    lib = api.load_library()
+    h = C.c_void_p()
+    assert lib.pt_scene_create(C.byref(h)) == -4          # PT_ERR_NO_DEVICE
+    assert b"no CUDA device" in lib.pt_last_error()
+    with pytest.raises(api.PtError):
+        api.Renderer()
+
+
+def test_product_does_not_touch_oracle():
+    """The oracle is test infrastructure: nothing under cpppathtracer_b200/ may import, load or link it."""
+    pkg = os.path.join(ROOT, "cpppathtracer_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")) or f == "Makefile":
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+                for needle in ("libpt_oracle", "ref_host", "_ref/", "pt_oracle", "libpt_ref"):
+                    assert needle not in src, (f, needle)
+
+
+def test_struct_layouts_match_header():
+    assert C.sizeof(api.PtMaterial) == 48 and C.sizeof(api.PtCamera) == 52
+    assert C.sizeof(api.PtStats) == 56
+
+
+def test_scene_generators_are_deterministic():
+    a, b = scenes.demo_scene(64, 36), scenes.demo_scene(64, 36)
+    for k in ("prim_type", "center", "radius", "y_pos", "height", "mat_idx", "materials"):
+        assert np.array_equal(getattr(a, k), getattr(b, k))
+    assert a.prim_type[0] == scenes.PLATFORM and a.n_prims >= 75
+    # quirk 7: hollow inner objects are spheres with radius 0.01 - r, even inside cylinders
+    inner = np.where(a.radius < 0)[0]
+    assert (a.prim_type[inner] == scenes.SPHERE).all()
+    assert (a.materials["type"][a.mat_idx[inner]] == scenes.GLASS).all()
+    c2 = scenes.sphere_field(1000)
+    assert c2.n_prims == 1001 and (c2.prim_type[1:] == scenes.SPHERE).all()
+    assert np.allclose(c2.center[1:, 1], c2.radius[1:])        # spheres rest on the floor
+    c3 = scenes.stress_field(2000)
+    glass = c3.materials["type"][c3.mat_idx] == scenes.GLASS
+    assert glass.mean() > 0.45 and (c3.prim_type == scenes.CYLINDER).mean() > 0.3
+
+
+def test_shard_samples_partitions_exactly():
+    for total in (0, 1, 7, 64, 1024, 1025):
+        for world in (1, 2, 3, 4, 8):
+            ranges = [ptd.shard_samples(total, world, r) for r in range(world)]
+            assert sum(c for _, c in ranges) == total
+            pos = 0
+            for first, count in ranges:
+                assert first == pos
+                pos += count
+            counts = [c for _, c in ranges]
+            assert max(counts) - min(counts) <= 1
+    with pytest.raises(ValueError):
+        ptd.shard_samples(8, 2, 2)
+
+
+def test_frame_round_robin():
+    for world in (1, 2, 4, 8):
+        owned = [ptd.frames_of_rank(120, world, r) for r in range(world)]
+        assert sorted(sum(owned, [])) == list(range(120))
+        assert max(len(o) for o in owned) - min(len(o) for o in owned) <= 1
+        assert all(ptd.frame_owner(f, world) == f % world for f in range(16))
+
+
+def test_mean_from_sum():
+    s = np.zeros((2, 2, 4), np.float32); s[..., :3] = 8.0; s[..., 3] = 4.0
+    assert np.array_equal(ptd.mean_from_sum(s), np.full((2, 2, 3), 2.0, np.float32))
