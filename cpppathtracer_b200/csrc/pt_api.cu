@@ -80,7 +80,8 @@ struct pt_scene {
     DevBuf<float> plat_y;
     DevBuf<int> plat_id, bvh_prims, parent_inner, parent_leaf, flags;
     DevBuf<int2> children;
-    DevBuf<uint32_t> codes, codes_sorted, ids, ids_sorted, bounds6, tie_rank;
+    DevBuf<uint32_t> codes, codes_sorted, ids, ids_sorted, bounds6;
+    DevBuf<int> orig_id;
     DevBuf<unsigned char> cub_tmp;
     int n_plat = 0, n_tree = 0, has_emitters = 0;
     Texture sky;
@@ -250,7 +251,12 @@ struct RefOrder {
 int upload_and_build(pt_scene* s) {
     const int n = (int)s->prims.size();
     cudaStream_t st = s->stream;
+    // device order = the reference's leaf visiting order, so that exact ties resolve by index (pt_wavefront.cuh)
+    std::vector<uint32_t> rank(std::max(n, 1));
+    if (s->opt_tie_order && n >= 2) rank = RefOrder(s->prims).ranks();
+    else for (int i = 0; i < n; ++i) rank[i] = (uint32_t)i;
     std::vector<float4> g0(std::max(n, 1)), g1(std::max(n, 1));
+    std::vector<int> orig(std::max(n, 1));
     std::vector<float> py; std::vector<int> pid, tree;
     s->has_emitters = 0;
     for (int i = 0; i < n; ++i) {
@@ -260,29 +266,26 @@ int upload_and_build(pt_scene* s) {
         uint32_t w = ((uint32_t)bin_of_material_type(m.type) << 28) | (uint32_t)p.mat_slot;
         float wf, tf; int ty = p.type;
         memcpy(&wf, &w, 4); memcpy(&tf, &ty, 4);
-        g0[i] = make_float4(p.c[0], p.c[1], p.c[2], p.radius);
-        g1[i] = make_float4(p.height, p.y_pos, tf, wf);
-        if (p.type == PT_PRIM_PLATFORM) { py.push_back(p.y_pos); pid.push_back(i); }
-        else if (p.type == PT_PRIM_SPHERE || p.type == PT_PRIM_CYLINDER) tree.push_back(i);
+        const int d = (int)rank[i];
+        g0[d] = make_float4(p.c[0], p.c[1], p.c[2], p.radius);
+        g1[d] = make_float4(p.height, p.y_pos, tf, wf);
+        orig[d] = i;
+    }
+    for (int d = 0; d < n; ++d) {
+        const HostPrim& p = s->prims[orig[d]];
+        if (p.type == PT_PRIM_PLATFORM) { py.push_back(p.y_pos); pid.push_back(d); }
+        else if (p.type == PT_PRIM_SPHERE || p.type == PT_PRIM_CYLINDER) tree.push_back(d);
     }
     std::vector<MaterialRec> recs(std::max<size_t>(s->materials.size(), 1));
     for (size_t i = 0; i < s->materials.size(); ++i) recs[i] = make_material_rec(s->materials[i]);
-    // tie ranks: only scenes with coplanar candidates (platforms / cylinders) can produce exact ties
-    std::vector<uint32_t> rank(std::max(n, 1));
-    bool need_ref_order = s->opt_tie_order && (int)tree.size() != n - (int)py.size() ? true : false;
-    int n_cyl = 0;
-    for (int i = 0; i < n; ++i) n_cyl += s->prims[i].type == PT_PRIM_CYLINDER;
-    need_ref_order = s->opt_tie_order && (n_cyl + (int)py.size() >= 2);
-    if (need_ref_order) rank = RefOrder(s->prims).ranks();
-    else for (int i = 0; i < n; ++i) rank[i] = (uint32_t)i;
 
     CK(s->geo0.reserve(g0.size())); CK(s->geo1.reserve(g1.size())); CK(s->mats.reserve(recs.size()));
-    CK(s->tie_rank.reserve(rank.size()));
+    CK(s->orig_id.reserve(orig.size()));
     CK(s->plat_y.reserve(std::max<size_t>(py.size(), 1))); CK(s->plat_id.reserve(std::max<size_t>(pid.size(), 1)));
     CK(cudaMemcpyAsync(s->geo0.p, g0.data(), g0.size() * sizeof(float4), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(s->geo1.p, g1.data(), g1.size() * sizeof(float4), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(s->mats.p, recs.data(), recs.size() * sizeof(MaterialRec), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(s->tie_rank.p, rank.data(), rank.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s->orig_id.p, orig.data(), orig.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     if (!py.empty()) {
         CK(cudaMemcpyAsync(s->plat_y.p, py.data(), py.size() * sizeof(float), cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(s->plat_id.p, pid.data(), pid.size() * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -336,7 +339,7 @@ int upload_and_build(pt_scene* s) {
 SceneDev scene_dev(pt_scene* s) {
     SceneDev d;
     d.nodes = s->nodes.p; d.geo0 = s->geo0.p; d.geo1 = s->geo1.p; d.mats = s->mats.p;
-    d.plat_y = s->plat_y.p; d.plat_id = s->plat_id.p; d.tie_rank = s->tie_rank.p;
+    d.plat_y = s->plat_y.p; d.plat_id = s->plat_id.p; d.orig_id = s->orig_id.p;
     d.n_plat = s->n_plat; d.n_tree_prims = s->n_tree; d.sky = s->sky.obj; d.has_emitters = s->has_emitters;
     return d;
 }
@@ -495,7 +498,7 @@ __global__ void k_unpack_hits(int n, SceneDev sc, const float4* __restrict__ ray
     float3 pos = f3(0, 0, 0), nrm = f3(0, 0, 0);
     if (h.y == PT_MISS_CODE) prim[i] = -1;
     else {
-        prim[i] = (int32_t)(h.y >> 3);
+        prim[i] = (int32_t)sc.orig_id[h.y >> 3];
         float4 o = ray_o[i], d = ray_d[i];
         hit_attributes(sc.geo0[h.y >> 3], (int)(h.y & 7u), f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), __uint_as_float(h.x), pos, nrm);
     }
@@ -609,7 +612,7 @@ void pt_scene_destroy(pt_scene* s) {
     s->inner_mn.release(); s->inner_mx.release(); s->mats.release(); s->plat_y.release(); s->plat_id.release();
     s->bvh_prims.release(); s->parent_inner.release(); s->parent_leaf.release(); s->flags.release(); s->children.release();
     s->codes.release(); s->codes_sorted.release(); s->ids.release(); s->ids_sorted.release(); s->bounds6.release();
-    s->tie_rank.release(); s->cub_tmp.release(); s->accum.release(); s->read_tmp.release(); s->path_out.release(); s->hit.release();
+    s->orig_id.release(); s->cub_tmp.release(); s->accum.release(); s->read_tmp.release(); s->path_out.release(); s->hit.release();
     s->bin_items.release(); s->ctrl.release(); s->seg_counter.release();
     for (int k = 0; k < 2; ++k) { s->q_o[k].release(); s->q_d[k].release(); s->q_thr[k].release(); s->scratch_i[k].release(); }
     for (auto& b : s->scratch_f) b.release();

@@ -28,6 +28,8 @@ struct BounceCtrl {
 };
 static_assert(sizeof(BounceCtrl) == 64, "control block is one 64-byte line");
 
+// Primitives live on the device in the reference's leaf VISITING order (or insertion order when
+// PT_OPT_TIE_ORDER is off): "device index" below always means that position.
 struct SceneDev {
     const float4* nodes;      // LBVH, 4 x float4 per inner node
     const float4* geo0;       // (cx, cy, cz, radius)
@@ -35,7 +37,7 @@ struct SceneDev {
     const MaterialRec* mats;
     const float* plat_y;      // platforms: side list tested for every ray
     const int* plat_id;
-    const uint32_t* tie_rank; // per primitive: position in the reference's leaf visiting order (or prim id)
+    const int* orig_id;       // device primitive index -> caller's primitive id (parity outputs only)
     int n_plat;
     int n_tree_prims;         // primitives in the LBVH (0: no tree)
     cudaTextureObject_t sky;
@@ -85,21 +87,22 @@ __device__ __forceinline__ TraceResult trace_closest(const SceneDev& sc, float3 
     float best_t = tmax;
     uint32_t best_code = PT_MISS_CODE;
     // Exact ties: the reference keeps whichever tied primitive its traversal meets first (strict `<` at
-    // object.cu:19,27,40,57,71,94,103).  Only coplanar parts tie in practice (a cylinder cap resting on a
-    // platform, video_renderer.cpp:78,105-106), so platforms and cylinders carry tie_rank[] = their position
-    // in the reference's leaf visiting order, and a tied candidate wins iff it outranks the current holder.
-    uint32_t best_rank = 0u;   // 0 = cannot be displaced (nothing yet, or a sphere)
-    auto tie_tmax = [&](uint32_t rank) -> float {
+    // object.cu:19,27,40,57,71,94,103).  Ties are not rare: far from the camera `b*b - a*c` (object.cu:16)
+    // cancels so coarsely that the two shells of a hollow glass sphere often get the same t, and cylinder
+    // caps rest exactly on the floor plane (video_renderer.cpp:78,105-106).  Device primitive indices ARE
+    // the reference's leaf visiting order (see upload_and_build), so a tied candidate wins iff its index
+    // is lower than the current holder's.
+    uint32_t best_idx = 0u;   // 0 = cannot be displaced (nothing yet, or the first-visited primitive)
+    auto tie_tmax = [&](uint32_t idx) -> float {
         // the tmax handed to the intersector: one ulp above best_t when this primitive outranks the holder,
         // so that `t < tmax` also admits t == best_t
-        return (rank < best_rank) ? __uint_as_float(__float_as_uint(best_t) + 1u) : best_t;
+        return (idx < best_idx) ? __uint_as_float(__float_as_uint(best_t) + 1u) : best_t;
     };
     // platforms first: they also give the tree walk an early upper bound
     for (int k = 0; k < sc.n_plat; ++k) {
         const uint32_t prim = (uint32_t)sc.plat_id[k];
-        const uint32_t rank = sc.tie_rank[prim];
-        float tm = tie_tmax(rank);
-        if (hit_platform(sc.plat_y[k], o, d, tmin, tm)) { best_t = tm; best_code = (prim << 3) | PART_PLATFORM; best_rank = rank; }
+        float tm = tie_tmax(prim);
+        if (hit_platform(sc.plat_y[k], o, d, tmin, tm)) { best_t = tm; best_code = (prim << 3) | PART_PLATFORM; best_idx = prim; }
     }
     if (sc.n_tree_prims > 0) {
         const float ix = 1.0f / (fabsf(d.x) > 1e-30f ? d.x : copysignf(1e-30f, d.x));
@@ -140,15 +143,11 @@ __device__ __forceinline__ TraceResult trace_closest(const SceneDev& sc, float3 
                 const uint32_t prim = leaf >> 2;
                 const float4 g0 = __ldg(&sc.geo0[prim]);
                 int part = 0;
-                if ((leaf & 3u) == 2u) {
-                    const uint32_t rank = __ldg(&sc.tie_rank[prim]);
-                    float tm = tie_tmax(rank);
-                    if (hit_cylinder(g0, __ldg(&sc.geo1[prim]).x, o, d, tmin, tm, part)) {
-                        best_t = tm; best_code = (prim << 3) | (uint32_t)part; best_rank = rank;
-                    }
-                } else {
-                    if (hit_sphere(g0, o, d, tmin, best_t, part)) { best_code = (prim << 3) | (uint32_t)part; best_rank = 0u; }
-                }
+                float tm = tie_tmax(prim);
+                bool h;
+                if ((leaf & 3u) == 2u) h = hit_cylinder(g0, __ldg(&sc.geo1[prim]).x, o, d, tmin, tm, part);
+                else h = hit_sphere(g0, o, d, tmin, tm, part);
+                if (h) { best_t = tm; best_code = (prim << 3) | (uint32_t)part; best_idx = prim; }
                 node = stack[--sp];
             }
         }
