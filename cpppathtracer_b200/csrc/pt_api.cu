@@ -74,6 +74,7 @@ struct pt_scene {
     int opt_stage_timing = 0;
     int opt_tie_order = 1;
     int opt_sky_quarter = 1;
+    int opt_refill_min = PT_REFILL_MIN, opt_steps_per_check = PT_STEPS_PER_CHECK, opt_inner_run = 4;
     // device scene
     DevBuf<float4> geo0, geo1, nodes, leaf_mn, leaf_mx, inner_mn, inner_mx;
     DevBuf<MaterialRec> mats;
@@ -375,7 +376,7 @@ int ensure_queues(pt_scene* s, uint32_t cap, int max_depth) {
 int launch_config(pt_scene* s) {
     if (s->grid_traverse) return PT_OK;
     int occ_t = 0, occ_s = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, k_traverse<false>, 128, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, k_traverse<false>, 32 * PT_TRAV_WARPS, 0));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_shade, 128, 0));
     s->grid_traverse = s->sm_count * std::max(occ_t, 1);
     s->grid_shade = s->sm_count * std::max(occ_s, 1);
@@ -419,9 +420,10 @@ int render_async(pt_scene* s, const pt_camera* cam, int spp, int max_depth, uint
         int cur = 0;
         for (int b = 0; b < max_depth; ++b) {
             CK(stage_event());
-            k_traverse<false><<<s->grid_traverse, 128, 0, st>>>(sd, s->q_o[cur].p, s->q_d[cur].p, nullptr,
+            k_traverse<false><<<s->grid_traverse, 32 * PT_TRAV_WARPS, 0, st>>>(sd, s->q_o[cur].p, s->q_d[cur].p, nullptr,
                                                                b == 0 ? 0.f : PT_BOUNCE_TMIN, s->ctrl.p + b, s->hit.p,
-                                                               s->bin_items.p, s->capacity);
+                                                               s->bin_items.p, s->capacity, (uint32_t)s->opt_refill_min,
+                                                               s->opt_steps_per_check, s->opt_inner_run);
             CK(stage_event());
             k_shade<<<s->grid_shade, 128, 0, st>>>(sd, key, npix, first_sample + s0, b, max_depth, s->q_o[cur].p,
                                                    s->q_d[cur].p, s->q_thr[cur].p, s->hit.p, s->bin_items.p, s->capacity,
@@ -483,7 +485,7 @@ int to_device(DevBuf<T>& buf, const T* host, size_t n, cudaStream_t st) {
 __global__ void k_pack_rays(int n, const float* __restrict__ rays8, float4* __restrict__ ray_o, float4* __restrict__ ray_d,
                             float2* __restrict__ range, BounceCtrl* __restrict__ ctrl) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) ctrl->in_count = (uint32_t)n;
+    if (i == 0) { ctrl->in_count.v = (uint32_t)n; ctrl->rays.v = (uint32_t)n; }
     if (i >= n) return;
     ray_o[i] = make_float4(rays8[8 * i], rays8[8 * i + 1], rays8[8 * i + 2], __uint_as_float((uint32_t)i));
     ray_d[i] = make_float4(rays8[8 * i + 3], rays8[8 * i + 4], rays8[8 * i + 5], 0.f);
@@ -632,6 +634,15 @@ int pt_set_option(pt_scene* s, int option, int64_t value) {
         case PT_OPT_STAGE_TIMING: s->opt_stage_timing = value != 0; return PT_OK;
         case PT_OPT_TIE_ORDER: s->opt_tie_order = value != 0; s->dirty = true; return PT_OK;
         case PT_OPT_SKY_QUARTER_ROWS: s->opt_sky_quarter = value != 0; return PT_OK;
+        case PT_OPT_TRAV_REFILL_MIN:
+            if (value < 1 || value > 32) return fail(PT_ERR_INVALID, "refill_min must be 1..32");
+            s->opt_refill_min = (int)value; return PT_OK;
+        case PT_OPT_TRAV_INNER_RUN:
+            if (value < 1 || value > 1024) return fail(PT_ERR_INVALID, "inner_run must be 1..1024");
+            s->opt_inner_run = (int)value; return PT_OK;
+        case PT_OPT_TRAV_STEPS:
+            if (value < 1 || value > 1024) return fail(PT_ERR_INVALID, "steps must be 1..1024");
+            s->opt_steps_per_check = (int)value; return PT_OK;
         default: return fail(PT_ERR_INVALID, "unknown option");
     }
 }
@@ -773,8 +784,9 @@ int pt_trace_rays(pt_scene* s, int n, const float* rays8, int32_t* prim, float* 
     CK(cudaMemsetAsync(s->ctrl.p, 0, 2 * sizeof(BounceCtrl), st));
     const int g = (n + 255) / 256;
     k_pack_rays<<<g, 256, 0, st>>>(n, s->scratch_f[0].p, s->q_o[0].p, s->q_d[0].p, (float2*)s->scratch_f[1].p, s->ctrl.p);
-    k_traverse<true><<<s->grid_traverse, 128, 0, st>>>(scene_dev(s), s->q_o[0].p, s->q_d[0].p, (const float2*)s->scratch_f[1].p,
-                                                      0.f, s->ctrl.p, s->hit.p, s->bin_items.p, s->capacity);
+    k_traverse<true><<<s->grid_traverse, 32 * PT_TRAV_WARPS, 0, st>>>(scene_dev(s), s->q_o[0].p, s->q_d[0].p, (const float2*)s->scratch_f[1].p,
+                                                      0.f, s->ctrl.p, s->hit.p, s->bin_items.p, s->capacity,
+                                                      (uint32_t)s->opt_refill_min, s->opt_steps_per_check, s->opt_inner_run);
     k_unpack_hits<<<g, 256, 0, st>>>(n, scene_dev(s), s->q_o[0].p, s->q_d[0].p, s->hit.p, s->scratch_i[0].p,
                                      s->scratch_f[2].p, s->scratch_f[3].p, s->scratch_f[4].p);
     s->stats.launches += 3;

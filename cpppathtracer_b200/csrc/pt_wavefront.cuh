@@ -17,16 +17,21 @@ namespace pt {
 
 #define PT_MISS_CODE 0xFFFFFFFFu
 #define PT_STACK 64
+#define PT_FULL 0xffffffffu
 
-// one control block per bounce, zeroed once per wave
+// One control block per bounce, zeroed once per wave.  Every counter that takes atomics sits on its own
+// 128-byte line (its own L2 slice queue): v1 kept them in one 64-byte line and k_shade spent its time
+// waiting on ~300 k same-line atomics per launch (profiles/r01_v1_summary.md).
+struct Counter128 { uint32_t v; uint32_t pad[31]; };
 struct BounceCtrl {
-    uint32_t in_count;            // rays in the input queue of this bounce
-    uint32_t trav_head;           // traversal work counter
-    uint32_t shade_head;          // shade work counter (in 32-item chunks)
-    uint32_t bin_count[NUM_BINS]; // items per shader bin
-    uint32_t pad[8];
+    Counter128 in_count;            // slots in the input queue of this bounce (holes included), written once
+    Counter128 rays;                // valid rays in that queue (statistics)
+    Counter128 trav_head;           // traversal work counter
+    Counter128 shade_head;          // shade work counter, in 32-item chunks
+    Counter128 bin_count[NUM_BINS]; // items per shader bin
 };
-static_assert(sizeof(BounceCtrl) == 64, "control block is one 64-byte line");
+static_assert(sizeof(BounceCtrl) == 128 * (4 + NUM_BINS), "one line per counter");
+#define PT_INVALID_SLOT 0xFFFFFFFFu   // ray_o.w of a queue slot whose path ended (hole)
 
 // Primitives live on the device in the reference's leaf VISITING order (or insertion order when
 // PT_OPT_TIE_ORDER is off): "device index" below always means that position.
@@ -75,124 +80,214 @@ __global__ void __launch_bounds__(256) k_raygen(CameraFrame cam, uint2 key, uint
         thr[pid] = make_float4(1.f, 1.f, 1.f, 0.f);
         if (zero_out) path_out[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) ctrl0->in_count = n_paths;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { ctrl0->in_count.v = n_paths; ctrl0->rays.v = n_paths; }
 }
 
 // ---- stage 1: closest hit ------------------------------------------------------------------------------
 // Replaces SceneBVH::TraceRay + Object::IntersectionTest (bvh.cu:167-205, object.cu:10-128): near-child-first
 // stack traversal of the 64-byte LBVH nodes, tagged sphere / cylinder leaf test, platforms from the side list.
-struct TraceResult { float t; uint32_t code; };
+//
+// Exact ties: the reference keeps whichever tied primitive its traversal meets first (strict `<` at
+// object.cu:19,27,40,57,71,94,103).  Ties are not rare: far from the camera `b*b - a*c` (object.cu:16) cancels
+// so coarsely that the two shells of a hollow glass sphere often get the same t, and cylinder caps rest exactly
+// on the floor plane (video_renderer.cpp:78,105-106).  Device primitive indices ARE the reference's leaf
+// visiting order (upload_and_build in pt_api.cu), so a tied candidate wins iff its index is lower than the
+// current holder's: the intersector is then handed a tmax one ulp above best_t, so its `t < tmax` admits t == best_t.
+// Persistent warps with lane refill: a lane whose ray finished takes the next ray of the queue while its
+// neighbours keep walking, so a warp no longer idles until its longest ray ends (v1: 12.7 of 32 lanes active
+// per instruction).  Finished rays are staged per warp in shared memory and binned by shader 32 at a time,
+// one atomic per warp and bin.
+#define PT_TRAV_WARPS 4
+#define PT_REFILL_MIN 32       // refill when at least this many lanes are idle (32: a warp refills as a whole;
+                               // measured on C2: partial refills gain nothing, profiles/r01_v2_sweep.md)
+#define PT_STEPS_PER_CHECK 8   // traversal rounds between two refill / retire checks
 
-__device__ __forceinline__ TraceResult trace_closest(const SceneDev& sc, float3 o, float3 d, float tmin, float tmax) {
-    float best_t = tmax;
-    uint32_t best_code = PT_MISS_CODE;
-    // Exact ties: the reference keeps whichever tied primitive its traversal meets first (strict `<` at
-    // object.cu:19,27,40,57,71,94,103).  Ties are not rare: far from the camera `b*b - a*c` (object.cu:16)
-    // cancels so coarsely that the two shells of a hollow glass sphere often get the same t, and cylinder
-    // caps rest exactly on the floor plane (video_renderer.cpp:78,105-106).  Device primitive indices ARE
-    // the reference's leaf visiting order (see upload_and_build), so a tied candidate wins iff its index
-    // is lower than the current holder's.
-    uint32_t best_idx = 0u;   // 0 = cannot be displaced (nothing yet, or the first-visited primitive)
-    auto tie_tmax = [&](uint32_t idx) -> float {
-        // the tmax handed to the intersector: one ulp above best_t when this primitive outranks the holder,
-        // so that `t < tmax` also admits t == best_t
-        return (idx < best_idx) ? __uint_as_float(__float_as_uint(best_t) + 1u) : best_t;
-    };
-    // platforms first: they also give the tree walk an early upper bound
+struct LaneRay {
+    float3 o, d;
+    float ix, iy, iz;      // 1/d
+    float ox, oy, oz;      // o/d, so that a slab plane distance is one FMA: plane*(1/d) - o/d
+    float slack;           // bound on the rounding error of those FMAs (added to the exit distance)
+    float tmin, best_t;
+    uint32_t best_code;
+    uint32_t slot;
+    int node, sp;
+};
+#define PT_SENTINEL 0x7fffffff
+
+__device__ __forceinline__ float tie_tmax(uint32_t idx, float best_t, uint32_t best_code) {
+    // see trace_closest: one ulp above best_t when primitive idx outranks the current holder
+    const uint32_t holder = (best_code == PT_MISS_CODE) ? 0u : (best_code >> 3);
+    return (idx < holder) ? __uint_as_float(__float_as_uint(best_t) + 1u) : best_t;
+}
+
+__device__ __forceinline__ void lane_begin(const SceneDev& sc, LaneRay& r, int* stack) {
+    r.best_code = PT_MISS_CODE;
     for (int k = 0; k < sc.n_plat; ++k) {
         const uint32_t prim = (uint32_t)sc.plat_id[k];
-        float tm = tie_tmax(prim);
-        if (hit_platform(sc.plat_y[k], o, d, tmin, tm)) { best_t = tm; best_code = (prim << 3) | PART_PLATFORM; best_idx = prim; }
+        float tm = tie_tmax(prim, r.best_t, r.best_code);
+        if (hit_platform(sc.plat_y[k], r.o, r.d, r.tmin, tm)) { r.best_t = tm; r.best_code = (prim << 3) | PART_PLATFORM; }
     }
-    if (sc.n_tree_prims > 0) {
-        const float ix = 1.0f / (fabsf(d.x) > 1e-30f ? d.x : copysignf(1e-30f, d.x));
-        const float iy = 1.0f / (fabsf(d.y) > 1e-30f ? d.y : copysignf(1e-30f, d.y));
-        const float iz = 1.0f / (fabsf(d.z) > 1e-30f ? d.z : copysignf(1e-30f, d.z));
-        int stack[PT_STACK];
-        int sp = 0;
-        int node = 0;
-        const int SENTINEL = 0x7fffffff;
-        stack[sp++] = SENTINEL;
-        while (node != SENTINEL) {
-            if (node >= 0) {
-                const float4 n0 = __ldg(&sc.nodes[4 * node + 0]);
-                const float4 n1 = __ldg(&sc.nodes[4 * node + 1]);
-                const float4 n2 = __ldg(&sc.nodes[4 * node + 2]);
-                const float4 n3 = __ldg(&sc.nodes[4 * node + 3]);
-                const float a0x = (n0.x - o.x) * ix, a1x = (n0.y - o.x) * ix;
-                const float a0y = (n0.z - o.y) * iy, a1y = (n0.w - o.y) * iy;
-                const float a0z = (n2.x - o.z) * iz, a1z = (n2.y - o.z) * iz;
-                const float b0x = (n1.x - o.x) * ix, b1x = (n1.y - o.x) * ix;
-                const float b0y = (n1.z - o.y) * iy, b1y = (n1.w - o.y) * iy;
-                const float b0z = (n2.z - o.z) * iz, b1z = (n2.w - o.z) * iz;
-                const float ea = fmaxf(fmaxf(fminf(a0x, a1x), fminf(a0y, a1y)), fmaxf(fminf(a0z, a1z), tmin));
-                const float xa = fminf(fminf(fmaxf(a0x, a1x), fmaxf(a0y, a1y)), fminf(fmaxf(a0z, a1z), best_t)) * 1.0000005f;
-                const float eb = fmaxf(fmaxf(fminf(b0x, b1x), fminf(b0y, b1y)), fmaxf(fminf(b0z, b1z), tmin));
-                const float xb = fminf(fminf(fmaxf(b0x, b1x), fmaxf(b0y, b1y)), fminf(fmaxf(b0z, b1z), best_t)) * 1.0000005f;
-                const bool ha = ea <= xa, hb = eb <= xb;
-                const int ca = __float_as_int(n3.x), cb = __float_as_int(n3.y);
-                if (ha && hb) {
-                    const bool a_near = ea <= eb;
-                    node = a_near ? ca : cb;
-                    stack[sp++] = a_near ? cb : ca;
-                } else if (ha) node = ca;
-                else if (hb) node = cb;
-                else node = stack[--sp];
-            } else {
-                const uint32_t leaf = (uint32_t)~node;
-                const uint32_t prim = leaf >> 2;
-                const float4 g0 = __ldg(&sc.geo0[prim]);
-                int part = 0;
-                float tm = tie_tmax(prim);
-                bool h;
-                if ((leaf & 3u) == 2u) h = hit_cylinder(g0, __ldg(&sc.geo1[prim]).x, o, d, tmin, tm, part);
-                else h = hit_sphere(g0, o, d, tmin, tm, part);
-                if (h) { best_t = tm; best_code = (prim << 3) | (uint32_t)part; best_idx = prim; }
-                node = stack[--sp];
+    r.ix = 1.0f / (fabsf(r.d.x) > 1e-30f ? r.d.x : copysignf(1e-30f, r.d.x));
+    r.iy = 1.0f / (fabsf(r.d.y) > 1e-30f ? r.d.y : copysignf(1e-30f, r.d.y));
+    r.iz = 1.0f / (fabsf(r.d.z) > 1e-30f ? r.d.z : copysignf(1e-30f, r.d.z));
+    r.ox = r.o.x * r.ix; r.oy = r.o.y * r.iy; r.oz = r.o.z * r.iz;
+    // |fma(p, 1/d, -o/d) - (p-o)/d| <= ~3 ulp of |o/d| (rounding of 1/d, of o/d and of the fma); culling only has
+    // to be conservative, so both interval ends get that much slack (plus the 4-ulp inflation of the leaf boxes)
+    r.slack = 4.0f * 1.1920929e-7f * fmaxf(fmaxf(fabsf(r.ox), fabsf(r.oy)), fabsf(r.oz));
+    r.sp = 0;
+    stack[r.sp++] = PT_SENTINEL;
+    r.node = sc.n_tree_prims > 0 ? 0 : PT_SENTINEL;
+}
+
+__device__ __forceinline__ void lane_inner(const SceneDev& sc, LaneRay& r, int* stack) {
+    {
+        const float4 n0 = __ldg(&sc.nodes[4 * r.node + 0]);
+        const float4 n1 = __ldg(&sc.nodes[4 * r.node + 1]);
+        const float4 n2 = __ldg(&sc.nodes[4 * r.node + 2]);
+        const float4 n3 = __ldg(&sc.nodes[4 * r.node + 3]);
+        const float a0x = fmaf(n0.x, r.ix, -r.ox), a1x = fmaf(n0.y, r.ix, -r.ox);
+        const float a0y = fmaf(n0.z, r.iy, -r.oy), a1y = fmaf(n0.w, r.iy, -r.oy);
+        const float a0z = fmaf(n2.x, r.iz, -r.oz), a1z = fmaf(n2.y, r.iz, -r.oz);
+        const float b0x = fmaf(n1.x, r.ix, -r.ox), b1x = fmaf(n1.y, r.ix, -r.ox);
+        const float b0y = fmaf(n1.z, r.iy, -r.oy), b1y = fmaf(n1.w, r.iy, -r.oy);
+        const float b0z = fmaf(n2.z, r.iz, -r.oz), b1z = fmaf(n2.w, r.iz, -r.oz);
+        const float lo = r.tmin - r.slack, hi = r.best_t * 1.0000005f + r.slack;
+        const float ea = fmaxf(fmaxf(fminf(a0x, a1x), fminf(a0y, a1y)), fmaxf(fminf(a0z, a1z), lo));
+        const float xa = fminf(fminf(fmaxf(a0x, a1x), fmaxf(a0y, a1y)), fminf(fmaxf(a0z, a1z), hi));
+        const float eb = fmaxf(fmaxf(fminf(b0x, b1x), fminf(b0y, b1y)), fmaxf(fminf(b0z, b1z), lo));
+        const float xb = fminf(fminf(fmaxf(b0x, b1x), fmaxf(b0y, b1y)), fminf(fmaxf(b0z, b1z), hi));
+        const bool ha = ea <= xa, hb = eb <= xb;
+        const int ca = __float_as_int(n3.x), cb = __float_as_int(n3.y);
+        if (ha && hb) {
+            const bool a_near = ea <= eb;
+            r.node = a_near ? ca : cb;
+            stack[r.sp++] = a_near ? cb : ca;
+        } else if (ha) r.node = ca;
+        else if (hb) r.node = cb;
+        else r.node = stack[--r.sp];
+    }
+}
+__device__ __forceinline__ void lane_leaf(const SceneDev& sc, LaneRay& r, int* stack) {
+    {
+        const uint32_t leaf = (uint32_t)~r.node;
+        const uint32_t prim = leaf >> 2;
+        const float4 g0 = __ldg(&sc.geo0[prim]);
+        int part = 0;
+        float tm = tie_tmax(prim, r.best_t, r.best_code);
+        bool h;
+        if ((leaf & 3u) == 2u) h = hit_cylinder(g0, __ldg(&sc.geo1[prim]).x, r.o, r.d, r.tmin, tm, part);
+        else h = hit_sphere(g0, r.o, r.d, r.tmin, tm, part);
+        if (h) { r.best_t = tm; r.best_code = (prim << 3) | (uint32_t)part; }
+        r.node = stack[--r.sp];
+    }
+}
+
+// bin the staged (bin<<29 | slot) entries of this warp, 32 at a time
+__device__ __forceinline__ void flush_stage(uint32_t* stage, uint32_t& stage_n, uint32_t lane, BounceCtrl* ctrl,
+                                            uint32_t* __restrict__ bin_items, uint32_t capacity, bool everything) {
+    while (stage_n >= 32u || (everything && stage_n > 0u)) {
+        const uint32_t cnt = stage_n < 32u ? stage_n : 32u;
+        const uint32_t e = lane < cnt ? stage[lane] : 0xFFFFFFFFu;
+        const int bin = lane < cnt ? (int)(e >> 29) : -1;
+#pragma unroll
+        for (int b = 0; b < NUM_BINS; ++b) {
+            const uint32_t m = __ballot_sync(PT_FULL, bin == b);
+            if (m) {
+                uint32_t off = 0;
+                const int leader = __ffs(m) - 1;
+                if ((int)lane == leader) off = atomicAdd(&ctrl->bin_count[b].v, (uint32_t)__popc(m));
+                off = __shfl_sync(PT_FULL, off, leader);
+                if (bin == b) bin_items[(size_t)b * capacity + off + __popc(m & ((1u << lane) - 1u))] = e & 0x1FFFFFFFu;
             }
         }
+        __syncwarp();
+        const uint32_t rest = stage_n - cnt;
+        const uint32_t moved = lane < rest ? stage[32u + lane] : 0u;
+        __syncwarp();
+        if (lane < rest) stage[lane] = moved;
+        stage_n = rest;
+        __syncwarp();
     }
-    TraceResult r; r.t = best_t; r.code = best_code;
-    return r;
 }
 
 template <bool PER_RAY_RANGE>
-__global__ void __launch_bounds__(128) k_traverse(SceneDev sc, const float4* __restrict__ ray_o,
-                                                  const float4* __restrict__ ray_d, const float2* __restrict__ ray_range,
-                                                  float tmin_all, BounceCtrl* __restrict__ ctrl,
-                                                  uint2* __restrict__ hit, uint32_t* __restrict__ bin_items,
-                                                  uint32_t capacity) {
+__global__ void __launch_bounds__(32 * PT_TRAV_WARPS) k_traverse(SceneDev sc, const float4* __restrict__ ray_o,
+                                                                const float4* __restrict__ ray_d,
+                                                                const float2* __restrict__ ray_range, float tmin_all,
+                                                                BounceCtrl* __restrict__ ctrl, uint2* __restrict__ hit,
+                                                                uint32_t* __restrict__ bin_items, uint32_t capacity,
+                                                                uint32_t refill_min, int steps_per_check, int inner_run) {
+    __shared__ uint32_t s_stage[PT_TRAV_WARPS][64];
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t n = ctrl->in_count;
+    uint32_t* stage = s_stage[threadIdx.x >> 5];
+    uint32_t stage_n = 0;
+    const uint32_t n = ctrl->in_count.v;
+    int stack[PT_STACK];
+    LaneRay r;
+    r.node = PT_SENTINEL; r.sp = 0; r.slot = 0; r.best_t = 0.f; r.best_code = PT_MISS_CODE; r.tmin = 0.f;
+    r.o = r.d = f3(0.f, 0.f, 0.f); r.ix = r.iy = r.iz = r.ox = r.oy = r.oz = r.slack = 0.f;
+    bool active = false;
+    bool exhausted = false;     // warp-uniform: the queue has no more rays to hand out
     while (true) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&ctrl->trav_head, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        const uint32_t slot = base + lane;
-        const bool valid = slot < n;
-        int bin = -1;
-        if (valid) {
-            const float4 o4 = ray_o[slot];
-            const float4 d4 = ray_d[slot];
-            float tmin = tmin_all, tmax = PT_TMAX;
-            if (PER_RAY_RANGE) { float2 r = ray_range[slot]; tmin = r.x; tmax = r.y; }
-            TraceResult r = trace_closest(sc, f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z), tmin, tmax);
-            hit[slot] = make_uint2(__float_as_uint(r.t), r.code);
-            bin = (r.code == PT_MISS_CODE) ? BIN_MISS : (int)(__float_as_uint(__ldg(&sc.geo1[r.code >> 3]).w) >> 28);
-        }
-        // bin the finished rays by shader: one atomic per warp and bin
-#pragma unroll
-        for (int b = 0; b < NUM_BINS; ++b) {
-            const uint32_t m = __ballot_sync(0xffffffffu, bin == b);
-            if (m) {
-                uint32_t off = 0;
-                if (lane == (uint32_t)(__ffs(m) - 1)) off = atomicAdd(&ctrl->bin_count[b], (uint32_t)__popc(m));
-                off = __shfl_sync(0xffffffffu, off, __ffs(m) - 1);
-                if (bin == b) bin_items[(size_t)b * capacity + off + __popc(m & ((1u << lane) - 1u))] = slot;
+        // ---- refill idle lanes ----
+        const uint32_t idle = __ballot_sync(PT_FULL, !active);
+        if (idle != 0u && !exhausted && ((uint32_t)__popc(idle) >= refill_min || idle == PT_FULL)) {
+            const uint32_t want = (uint32_t)__popc(idle);
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&ctrl->trav_head.v, want);
+            base = __shfl_sync(PT_FULL, base, 0);
+            if (base + want >= n) exhausted = true;
+            if (!active) {
+                const uint32_t slot = base + __popc(idle & ((1u << lane) - 1u));
+                if (slot < n) {
+                    const float4 o4 = ray_o[slot];
+                    if (__float_as_uint(o4.w) != PT_INVALID_SLOT) {
+                        const float4 d4 = ray_d[slot];
+                        r.o = f3(o4.x, o4.y, o4.z); r.d = f3(d4.x, d4.y, d4.z);
+                        r.tmin = tmin_all; r.best_t = PT_TMAX;
+                        if (PER_RAY_RANGE) { const float2 rr = ray_range[slot]; r.tmin = rr.x; r.best_t = rr.y; }
+                        r.slot = slot;
+                        lane_begin(sc, r, stack);
+                        active = true;
+                    }
+                }
             }
         }
+        if (!__any_sync(PT_FULL, active)) {
+            if (exhausted) break;
+            continue;                       // a refill that only found holes: fetch again
+        }
+        // ---- walk ----
+        // while-while: a lane first runs down inner nodes (up to inner_run of them), then tests the leaf it
+        // reached; the warp reconverges between the two so node steps and primitive tests each run with as many
+        // lanes as possible instead of interleaving (v1 "if-if": 12.7 of 32 lanes active per instruction)
+#pragma unroll 1
+        for (int it = 0; it < steps_per_check; ++it) {
+            if (active) {
+                int k = 0;
+#pragma unroll 1
+                while (r.node >= 0 && r.node != PT_SENTINEL && k < inner_run) { lane_inner(sc, r, stack); ++k; }
+            }
+            if (active && r.node < 0) lane_leaf(sc, r, stack);
+        }
+        // ---- retire finished lanes ----
+        const bool fin = active && r.node == PT_SENTINEL;
+        const uint32_t fm = __ballot_sync(PT_FULL, fin);
+        if (fm) {
+            if (fin) {
+                hit[r.slot] = make_uint2(__float_as_uint(r.best_t), r.best_code);
+                const uint32_t bin = (r.best_code == PT_MISS_CODE)
+                                         ? (uint32_t)BIN_MISS
+                                         : (__float_as_uint(__ldg(&sc.geo1[r.best_code >> 3]).w) >> 28);
+                stage[stage_n + __popc(fm & ((1u << lane) - 1u))] = (bin << 29) | r.slot;
+                active = false;
+            }
+            stage_n += (uint32_t)__popc(fm);
+            __syncwarp();
+            flush_stage(stage, stage_n, lane, ctrl, bin_items, capacity, false);
+        }
     }
+    flush_stage(stage, stage_n, lane, ctrl, bin_items, capacity, true);
 }
 
 // ---- stage 2: shade / miss, binned by shader; survivors are compacted into the next ray queue ------------
@@ -207,74 +302,95 @@ __global__ void __launch_bounds__(128) k_shade(SceneDev sc, uint2 key, uint32_t 
                                                float4* __restrict__ out_d, float4* __restrict__ out_thr,
                                                float4* __restrict__ path_out) {
     const uint32_t lane = threadIdx.x & 31u;
-    uint32_t chunk_end[NUM_BINS];
-    uint32_t total = 0;
+    // Work items are 32-item chunks of the five shader bins, so a warp never mixes shaders.  The output slot of
+    // a hit item is a pure function of (bin, item): next queue = [diffuse | glossy | mix | glass] survivors in bin
+    // order.  No atomics for the compaction (v1 took one same-address atomic per warp here); the few paths that
+    // die with zero throughput leave a hole marked PT_INVALID_SLOT that the next traversal skips.
+    uint32_t chunk_end[NUM_BINS], bin_n[NUM_BINS], out_base[NUM_BINS];
+    uint32_t total = 0, next_n = 0;
 #pragma unroll
-    for (int b = 0; b < NUM_BINS; ++b) { total += (ctrl->bin_count[b] + 31u) >> 5; chunk_end[b] = total; }
+    for (int b = 0; b < NUM_BINS; ++b) {
+        bin_n[b] = ctrl->bin_count[b].v;
+        total += (bin_n[b] + 31u) >> 5; chunk_end[b] = total;
+        out_base[b] = next_n;
+        if (b != BIN_MISS) next_n += bin_n[b];
+    }
+    const bool last_bounce = bounce + 1 >= max_depth;
+    if (!last_bounce && blockIdx.x == 0 && threadIdx.x == 0) ctrl_next->in_count.v = next_n;
+    // chunks taken per atomic: enough work per grab to keep the head counter cold, small enough to balance the tail
+    const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
+    uint32_t grab = total / (n_warps * 4u);
+    grab = grab < 1u ? 1u : (grab > 8u ? 8u : grab);
+    uint32_t alive_count = 0;
     while (true) {
-        uint32_t chunk = 0;
-        if (lane == 0) chunk = atomicAdd(&ctrl->shade_head, 1u);
-        chunk = __shfl_sync(0xffffffffu, chunk, 0);
-        if (chunk >= total) break;
-        int bin = 0;
+        uint32_t first = 0;
+        if (lane == 0) first = atomicAdd(&ctrl->shade_head.v, grab);
+        first = __shfl_sync(PT_FULL, first, 0);
+        if (first >= total) break;
+        const uint32_t end = first + grab < total ? first + grab : total;
+        for (uint32_t chunk = first; chunk < end; ++chunk) {
+            int bin = 0;
+            uint32_t first_chunk = 0u, n_bin = bin_n[0], base_bin = out_base[0];
 #pragma unroll
-        for (int b = 0; b < NUM_BINS - 1; ++b) bin += (chunk >= chunk_end[b]) ? 1 : 0;
-        const uint32_t first_chunk = bin ? chunk_end[bin - 1] : 0u;
-        const uint32_t item = ((chunk - first_chunk) << 5) + lane;
-        const bool valid = item < ctrl->bin_count[bin];
-        bool alive = false;
-        float3 pos = f3(0, 0, 0), ndir = f3(0, 0, 0), thr = f3(0, 0, 0);
-        uint32_t pixel = 0, s = 0;
-        if (valid) {
+            for (int b = 1; b < NUM_BINS; ++b)
+                if (chunk >= chunk_end[b - 1]) { bin = b; first_chunk = chunk_end[b - 1]; n_bin = bin_n[b]; base_bin = out_base[b]; }
+            const uint32_t item = ((chunk - first_chunk) << 5) + lane;
+            const bool valid = item < n_bin;
+            if (!valid) continue;
             const uint32_t slot = bin_items[(size_t)bin * capacity + item];
             const float4 o4 = ray_o[slot];
             const float4 d4 = ray_d[slot];
             const float4 t4 = thr_in[slot];
             const uint2 h = hit[slot];
-            pixel = __float_as_uint(o4.w);
-            s = __float_as_uint(d4.w);
+            const uint32_t pixel = __float_as_uint(o4.w);
+            const uint32_t s = __float_as_uint(d4.w);
             const size_t pid = (size_t)s * npix + pixel;
             const float3 o = f3(o4.x, o4.y, o4.z), d = f3(d4.x, d4.y, d4.z);
-            thr = f3(t4.x, t4.y, t4.z);
+            float3 thr = f3(t4.x, t4.y, t4.z);
             if (bin == BIN_MISS) {
                 const float3 c = thr * sky_radiance(sc.sky, d);
                 if (sc.has_emitters) { float4 p = path_out[pid]; path_out[pid] = make_float4(p.x + c.x, p.y + c.y, p.z + c.z, 0.f); }
                 else path_out[pid] = make_float4(c.x, c.y, c.z, 0.f);
-            } else {
-                const uint32_t prim = h.y >> 3;
-                const float4 g0 = __ldg(&sc.geo0[prim]);
-                const uint32_t mslot = __float_as_uint(__ldg(&sc.geo1[prim]).w) & 0x0fffffffu;
-                const MaterialRec m = sc.mats[mslot];
-                float3 normal;
-                hit_attributes(g0, (int)(h.y & 7u), o, d, __uint_as_float(h.x), pos, normal);
-                const float4 U = philox_uniform4(key, pixel, first_sample + s, 1u + (uint32_t)bounce);
-                Scatter sct;
-                shade_bin(bin, m, normal, d, U, sct);
-                if (sc.has_emitters) {
-                    const float3 c = thr * sct.radiance;
-                    float4 p = path_out[pid];
-                    path_out[pid] = make_float4(p.x + c.x, p.y + c.y, p.z + c.z, 0.f);
+                continue;
+            }
+            const uint32_t prim = h.y >> 3;
+            const float4 g0 = __ldg(&sc.geo0[prim]);
+            const uint32_t mslot = __float_as_uint(__ldg(&sc.geo1[prim]).w) & 0x0fffffffu;
+            const MaterialRec m = sc.mats[mslot];
+            float3 pos, normal;
+            hit_attributes(g0, (int)(h.y & 7u), o, d, __uint_as_float(h.x), pos, normal);
+            const float4 U = philox_uniform4(key, pixel, first_sample + s, 1u + (uint32_t)bounce);
+            Scatter sct;
+            shade_bin(bin, m, normal, d, U, sct);
+            if (sc.has_emitters) {
+                const float3 c = thr * sct.radiance;
+                float4 p = path_out[pid];
+                path_out[pid] = make_float4(p.x + c.x, p.y + c.y, p.z + c.z, 0.f);
+            }
+            thr = thr * sct.atten;
+            // a path whose throughput is exactly zero can add nothing more (finite sky and emission):
+            // ending it here is result-identical to the reference, which keeps bouncing it (path_tracer.cu:141-170)
+            const bool alive = !last_bounce && (thr.x != 0.f || thr.y != 0.f || thr.z != 0.f);
+            if (!alive && !sc.has_emitters) path_out[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!last_bounce) {
+                const uint32_t j = base_bin + item;
+                if (alive) {
+                    const float3 ndir = normalize(sct.bounce);
+                    out_o[j] = make_float4(pos.x, pos.y, pos.z, __uint_as_float(pixel));
+                    out_d[j] = make_float4(ndir.x, ndir.y, ndir.z, __uint_as_float(s));
+                    out_thr[j] = make_float4(thr.x, thr.y, thr.z, 0.f);
+                    ++alive_count;
+                } else {
+                    out_o[j] = make_float4(0.f, 0.f, 0.f, __uint_as_float(PT_INVALID_SLOT));
                 }
-                thr = thr * sct.atten;
-                ndir = normalize(sct.bounce);
-                // a path whose throughput is exactly zero can add nothing more (finite sky and emission):
-                // ending it here is result-identical to the reference, which keeps bouncing it (path_tracer.cu:141-170)
-                alive = (bounce + 1 < max_depth) && (thr.x != 0.f || thr.y != 0.f || thr.z != 0.f);
-                if (!alive && !sc.has_emitters) path_out[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
-        const uint32_t m = __ballot_sync(0xffffffffu, alive);
-        if (m) {
-            uint32_t off = 0;
-            if (lane == (uint32_t)(__ffs(m) - 1)) off = atomicAdd(&ctrl_next->in_count, (uint32_t)__popc(m));
-            off = __shfl_sync(0xffffffffu, off, __ffs(m) - 1);
-            if (alive) {
-                const uint32_t j = off + __popc(m & ((1u << lane) - 1u));
-                out_o[j] = make_float4(pos.x, pos.y, pos.z, __uint_as_float(pixel));
-                out_d[j] = make_float4(ndir.x, ndir.y, ndir.z, __uint_as_float(s));
-                out_thr[j] = make_float4(thr.x, thr.y, thr.z, 0.f);
-            }
-        }
+    }
+    // statistics: valid rays handed to the next bounce (one atomic per warp per launch)
+    if (!last_bounce) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) alive_count += __shfl_xor_sync(PT_FULL, alive_count, o);
+        if (lane == 0 && alive_count) atomicAdd(&ctrl_next->rays.v, alive_count);
     }
 }
 
@@ -298,7 +414,7 @@ __global__ void __launch_bounds__(256) k_accumulate(uint32_t npix, uint32_t n_sa
 // per-wave bookkeeping: rays traced = sum of the bounce input queues (diagnostic counter, 1 thread)
 __global__ void k_wave_stats(int max_depth, const BounceCtrl* __restrict__ ctrl, unsigned long long* __restrict__ segments) {
     unsigned long long n = 0;
-    for (int b = 0; b < max_depth; ++b) n += ctrl[b].in_count;
+    for (int b = 0; b < max_depth; ++b) n += ctrl[b].rays.v;
     *segments += n;
 }
 

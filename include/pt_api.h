@@ -78,8 +78,11 @@ enum {
     PT_OPT_STAGE_TIMING = 2,  /* 1: record per-stage CUDA events (adds syncs at frame end only)    */
     PT_OPT_TIE_ORDER = 3,     /* 1 (default): exactly tied hits resolve in the reference's leaf
                                  visiting order (bvh.cu:31-90,167-205); 0: lowest primitive id wins */
-    PT_OPT_SKY_QUARTER_ROWS = 4 /* 1 (default): reproduce the reference's upload that copies `width`
+    PT_OPT_SKY_QUARTER_ROWS = 4, /* 1 (default): reproduce the reference's upload that copies `width`
                                  BYTES per row (cuSrc/textures.cu:32); 0: upload whole rows         */
+    PT_OPT_TRAV_REFILL_MIN = 5, /* tuning: idle lanes per warp that trigger a ray refill (1..32)     */
+    PT_OPT_TRAV_STEPS = 6,      /* tuning: traversal rounds between two refill / retire checks       */
+    PT_OPT_TRAV_INNER_RUN = 7   /* tuning: inner-node steps a lane may take before the warp regroups for leaf tests */
 };
 
 /* ---- lifetime -------------------------------------------------------------------------------- */
