@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpt_b200.so")
 
 PT_OPT_WAVE_PATHS, PT_OPT_STAGE_TIMING, PT_OPT_TIE_ORDER, PT_OPT_SKY_QUARTER_ROWS = 1, 2, 3, 4
-PT_OPT_TRAV_REFILL_MIN, PT_OPT_TRAV_STEPS, PT_OPT_TRAV_INNER_RUN = 5, 6, 7
+PT_OPT_TRAV_REFILL_MIN, PT_OPT_TRAV_STEPS, PT_OPT_TRAV_INNER_RUN, PT_OPT_COUNT_STEPS = 5, 6, 7, 8
 
 
 class PtMaterial(C.Structure):
@@ -34,7 +34,7 @@ class PtStats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("segments", C.c_uint64), ("launches", C.c_uint64), ("render_ms", C.c_float),
                 ("traverse_ms", C.c_float), ("shade_ms", C.c_float), ("build_ms", C.c_float),
                 ("bvh_nodes", C.c_uint32), ("wave_paths", C.c_uint32), ("traverse_launches", C.c_uint32),
-                ("waves", C.c_uint32)]
+                ("waves", C.c_uint32), ("node_steps", C.c_uint64), ("prim_tests", C.c_uint64)]
 
 
 EXPORTS = [

@@ -13,6 +13,7 @@
 #include "pt_lbvh.cuh"
 #include "pt_math.cuh"
 #include "pt_wavefront.cuh"
+#include "pt_display.cuh"
 
 using namespace pt;
 
@@ -74,6 +75,7 @@ struct pt_scene {
     int opt_stage_timing = 0;
     int opt_tie_order = 1;
     int opt_sky_quarter = 1;
+    int opt_count_steps = 0;
     int opt_refill_min = PT_REFILL_MIN, opt_steps_per_check = PT_STEPS_PER_CHECK, opt_inner_run = 4;
     // device scene
     DevBuf<float4> geo0, geo1, nodes, leaf_mn, leaf_mx, inner_mn, inner_mx;
@@ -369,21 +371,22 @@ int ensure_queues(pt_scene* s, uint32_t cap, int max_depth) {
         s->capacity = cap;
     }
     CK(s->ctrl.reserve((size_t)max_depth + 2));
-    CK(s->seg_counter.reserve(1));
+    CK(s->seg_counter.reserve(4));
     return PT_OK;
 }
 
 int launch_config(pt_scene* s) {
     if (s->grid_traverse) return PT_OK;
     int occ_t = 0, occ_s = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, k_traverse<false>, 32 * PT_TRAV_WARPS, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, k_traverse<false, false>, 32 * PT_TRAV_WARPS, 0));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_shade, 128, 0));
     s->grid_traverse = s->sm_count * std::max(occ_t, 1);
     s->grid_shade = s->sm_count * std::max(occ_s, 1);
     return PT_OK;
 }
 
-int render_async(pt_scene* s, const pt_camera* cam, int spp, int max_depth, uint64_t seed, uint32_t first_sample) {
+int render_async(pt_scene* s, const pt_camera* cam, int spp, int max_depth, uint64_t seed, uint32_t first_sample,
+                 bool accumulate = true, float4* gbuf_normal = nullptr) {
     if (!s || !cam) return fail(PT_ERR_INVALID, "null argument");
     if (!s->built || s->dirty) return fail(PT_ERR_NOT_BUILT, "pt_build must be called after the scene changed");
     if (spp <= 0 || max_depth <= 0 || max_depth > 64) return fail(PT_ERR_INVALID, "bad spp / max_depth");
@@ -406,7 +409,7 @@ int render_async(pt_scene* s, const pt_camera* cam, int spp, int max_depth, uint
         if (ev_i >= s->stage_events.size()) { cudaEvent_t e; cudaError_t r = cudaEventCreate(&e); if (r) return r; s->stage_events.push_back(e); }
         return cudaEventRecord(s->stage_events[ev_i++], st);
     };
-    CK(cudaMemsetAsync(s->seg_counter.p, 0, sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(s->seg_counter.p, 0, 4 * sizeof(unsigned long long), st));
     CK(cudaEventRecord(s->ev0, st));
     uint64_t launches = 0;
     for (uint32_t s0 = 0; s0 < (uint32_t)spp; s0 += spp_per_wave) {
@@ -420,21 +423,27 @@ int render_async(pt_scene* s, const pt_camera* cam, int spp, int max_depth, uint
         int cur = 0;
         for (int b = 0; b < max_depth; ++b) {
             CK(stage_event());
-            k_traverse<false><<<s->grid_traverse, 32 * PT_TRAV_WARPS, 0, st>>>(sd, s->q_o[cur].p, s->q_d[cur].p, nullptr,
-                                                               b == 0 ? 0.f : PT_BOUNCE_TMIN, s->ctrl.p + b, s->hit.p,
-                                                               s->bin_items.p, s->capacity, (uint32_t)s->opt_refill_min,
-                                                               s->opt_steps_per_check, s->opt_inner_run);
+            if (s->opt_count_steps)
+                k_traverse<false, true><<<s->grid_traverse, 32 * PT_TRAV_WARPS, 0, st>>>(
+                    sd, s->q_o[cur].p, s->q_d[cur].p, nullptr, b == 0 ? 0.f : PT_BOUNCE_TMIN, s->ctrl.p + b, s->hit.p,
+                    s->bin_items.p, s->capacity, (uint32_t)s->opt_refill_min, s->opt_steps_per_check, s->opt_inner_run,
+                    s->seg_counter.p + 1);
+            else
+                k_traverse<false, false><<<s->grid_traverse, 32 * PT_TRAV_WARPS, 0, st>>>(
+                    sd, s->q_o[cur].p, s->q_d[cur].p, nullptr, b == 0 ? 0.f : PT_BOUNCE_TMIN, s->ctrl.p + b, s->hit.p,
+                    s->bin_items.p, s->capacity, (uint32_t)s->opt_refill_min, s->opt_steps_per_check, s->opt_inner_run,
+                    nullptr);
             CK(stage_event());
             k_shade<<<s->grid_shade, 128, 0, st>>>(sd, key, npix, first_sample + s0, b, max_depth, s->q_o[cur].p,
                                                    s->q_d[cur].p, s->q_thr[cur].p, s->hit.p, s->bin_items.p, s->capacity,
                                                    s->ctrl.p + b, s->ctrl.p + b + 1, s->q_o[cur ^ 1].p, s->q_d[cur ^ 1].p,
-                                                   s->q_thr[cur ^ 1].p, s->path_out.p);
+                                                   s->q_thr[cur ^ 1].p, s->path_out.p, gbuf_normal);
             launches += 2;
             cur ^= 1;
         }
         CK(stage_event());
         const int ac_grid = (int)std::min<uint32_t>((npix + 255u) / 256u, (uint32_t)s->sm_count * 8u);
-        k_accumulate<<<ac_grid, 256, 0, st>>>(npix, ns, s->path_out.p, s->accum.p);
+        if (accumulate) k_accumulate<<<ac_grid, 256, 0, st>>>(npix, ns, s->path_out.p, s->accum.p);
         k_wave_stats<<<1, 1, 0, st>>>(max_depth, s->ctrl.p, s->seg_counter.p);
         launches += 2;
         CK(cudaGetLastError());
@@ -453,11 +462,11 @@ int render_async(pt_scene* s, const pt_camera* cam, int spp, int max_depth, uint
 int finish_frame(pt_scene* s, int max_depth_hint) {
     (void)max_depth_hint;
     if (!s->frame_recorded) { CK(cudaStreamSynchronize(s->stream)); return PT_OK; }
-    unsigned long long seg = 0;
-    CK(cudaMemcpyAsync(&seg, s->seg_counter.p, sizeof(seg), cudaMemcpyDeviceToHost, s->stream));
+    unsigned long long seg4[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyAsync(seg4, s->seg_counter.p, sizeof(seg4), cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     CK(cudaEventElapsedTime(&s->stats.render_ms, s->ev0, s->ev1));
-    s->stats.segments = seg;
+    s->stats.segments = seg4[0]; s->stats.node_steps = seg4[1]; s->stats.prim_tests = seg4[2];
     if (s->opt_stage_timing && s->stage_events.size() >= 2) {
         // events alternate: [traverse start, shade start] per bounce, then accumulate start, per wave
         float trav = 0.f, shade = 0.f;
@@ -578,8 +587,32 @@ void destroy_texture(Texture& t) {
     t.obj = 0; t.arr = nullptr;
 }
 
-int display_dispatch(pt_scene*, const pt_camera*, int, uint64_t, uint32_t, uint8_t*, size_t) {
-    return fail(PT_ERR_INVALID, "pt_dispatch_ray: display pipeline not built yet");
+// One iteration of the reference's PipelineLoop (cuSrc/path_tracer.cu:256-306) minus the host thread:
+// one sample per pixel -> Denoising -> Mix -> BGRA8 -> D2H.  sample_idx is the reference's 1-based
+// cur_sample_idx_ (motional_camera.cu:195): 1 restarts the running mean, like MotionalCamera::Refresh.
+int display_dispatch(pt_scene* s, const pt_camera* cam, int max_depth, uint64_t seed, uint32_t sample_idx,
+                     uint8_t* bgra_out, size_t nbytes) {
+    if (!s || !cam || !bgra_out) return fail(PT_ERR_INVALID, "null argument");
+    if (sample_idx < 1) return fail(PT_ERR_INVALID, "sample_idx is 1-based");
+    const size_t npix = (size_t)cam->width * cam->height;
+    if (nbytes != npix * 4) return fail(PT_ERR_INVALID, "nbytes must be 4*width*height");
+    if (cam->width != s->disp_w || cam->height != s->disp_h) {
+        s->disp_mix.release(); s->disp_normal.release(); s->disp_bgra.release();
+        CK(s->disp_mix.reserve(npix)); CK(s->disp_normal.reserve(npix)); CK(s->disp_bgra.reserve(npix * 4));
+        CK(cudaMemsetAsync(s->disp_mix.p, 0, npix * sizeof(float4), s->stream));
+        s->disp_w = cam->width; s->disp_h = cam->height;
+    }
+    const uint32_t saved_wave = s->opt_wave_paths;
+    int rc = render_async(s, cam, 1, max_depth, seed, sample_idx - 1, /*accumulate=*/false, s->disp_normal.p);
+    s->opt_wave_paths = saved_wave;
+    if (rc) return rc;
+    dim3 tb(32, 8), gb((cam->width + 31) / 32, (cam->height + 7) / 8);
+    k_denoise_mix<<<gb, tb, 0, s->stream>>>(cam->width, cam->height, s->path_out.p, s->disp_normal.p, s->disp_mix.p,
+                                            s->disp_bgra.p, (int)sample_idx);
+    s->stats.launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(bgra_out, s->disp_bgra.p, npix * 4, cudaMemcpyDeviceToHost, s->stream));
+    return finish_frame(s, max_depth);
 }
 
 }  // namespace
@@ -637,6 +670,7 @@ int pt_set_option(pt_scene* s, int option, int64_t value) {
         case PT_OPT_TRAV_REFILL_MIN:
             if (value < 1 || value > 32) return fail(PT_ERR_INVALID, "refill_min must be 1..32");
             s->opt_refill_min = (int)value; return PT_OK;
+        case PT_OPT_COUNT_STEPS: s->opt_count_steps = value != 0; return PT_OK;
         case PT_OPT_TRAV_INNER_RUN:
             if (value < 1 || value > 1024) return fail(PT_ERR_INVALID, "inner_run must be 1..1024");
             s->opt_inner_run = (int)value; return PT_OK;
@@ -784,9 +818,9 @@ int pt_trace_rays(pt_scene* s, int n, const float* rays8, int32_t* prim, float* 
     CK(cudaMemsetAsync(s->ctrl.p, 0, 2 * sizeof(BounceCtrl), st));
     const int g = (n + 255) / 256;
     k_pack_rays<<<g, 256, 0, st>>>(n, s->scratch_f[0].p, s->q_o[0].p, s->q_d[0].p, (float2*)s->scratch_f[1].p, s->ctrl.p);
-    k_traverse<true><<<s->grid_traverse, 32 * PT_TRAV_WARPS, 0, st>>>(scene_dev(s), s->q_o[0].p, s->q_d[0].p, (const float2*)s->scratch_f[1].p,
-                                                      0.f, s->ctrl.p, s->hit.p, s->bin_items.p, s->capacity,
-                                                      (uint32_t)s->opt_refill_min, s->opt_steps_per_check, s->opt_inner_run);
+    k_traverse<true, false><<<s->grid_traverse, 32 * PT_TRAV_WARPS, 0, st>>>(
+        scene_dev(s), s->q_o[0].p, s->q_d[0].p, (const float2*)s->scratch_f[1].p, 0.f, s->ctrl.p, s->hit.p, s->bin_items.p,
+        s->capacity, (uint32_t)s->opt_refill_min, s->opt_steps_per_check, s->opt_inner_run, nullptr);
     k_unpack_hits<<<g, 256, 0, st>>>(n, scene_dev(s), s->q_o[0].p, s->q_d[0].p, s->hit.p, s->scratch_i[0].p,
                                      s->scratch_f[2].p, s->scratch_f[3].p, s->scratch_f[4].p);
     s->stats.launches += 3;

@@ -210,13 +210,14 @@ __device__ __forceinline__ void flush_stage(uint32_t* stage, uint32_t& stage_n, 
     }
 }
 
-template <bool PER_RAY_RANGE>
+template <bool PER_RAY_RANGE, bool COUNT_STEPS>
 __global__ void __launch_bounds__(32 * PT_TRAV_WARPS) k_traverse(SceneDev sc, const float4* __restrict__ ray_o,
                                                                 const float4* __restrict__ ray_d,
                                                                 const float2* __restrict__ ray_range, float tmin_all,
                                                                 BounceCtrl* __restrict__ ctrl, uint2* __restrict__ hit,
                                                                 uint32_t* __restrict__ bin_items, uint32_t capacity,
-                                                                uint32_t refill_min, int steps_per_check, int inner_run) {
+                                                                uint32_t refill_min, int steps_per_check, int inner_run,
+                                                                unsigned long long* __restrict__ step_counters) {
     __shared__ uint32_t s_stage[PT_TRAV_WARPS][64];
     const uint32_t lane = threadIdx.x & 31u;
     uint32_t* stage = s_stage[threadIdx.x >> 5];
@@ -228,6 +229,7 @@ __global__ void __launch_bounds__(32 * PT_TRAV_WARPS) k_traverse(SceneDev sc, co
     r.o = r.d = f3(0.f, 0.f, 0.f); r.ix = r.iy = r.iz = r.ox = r.oy = r.oz = r.slack = 0.f;
     bool active = false;
     bool exhausted = false;     // warp-uniform: the queue has no more rays to hand out
+    uint32_t n_inner = 0, n_leaf = 0;   // COUNT_STEPS only
     while (true) {
         // ---- refill idle lanes ----
         const uint32_t idle = __ballot_sync(PT_FULL, !active);
@@ -266,9 +268,9 @@ __global__ void __launch_bounds__(32 * PT_TRAV_WARPS) k_traverse(SceneDev sc, co
             if (active) {
                 int k = 0;
 #pragma unroll 1
-                while (r.node >= 0 && r.node != PT_SENTINEL && k < inner_run) { lane_inner(sc, r, stack); ++k; }
+                while (r.node >= 0 && r.node != PT_SENTINEL && k < inner_run) { lane_inner(sc, r, stack); ++k; if (COUNT_STEPS) ++n_inner; }
             }
-            if (active && r.node < 0) lane_leaf(sc, r, stack);
+            if (active && r.node < 0) { lane_leaf(sc, r, stack); if (COUNT_STEPS) ++n_leaf; }
         }
         // ---- retire finished lanes ----
         const bool fin = active && r.node == PT_SENTINEL;
@@ -288,6 +290,11 @@ __global__ void __launch_bounds__(32 * PT_TRAV_WARPS) k_traverse(SceneDev sc, co
         }
     }
     flush_stage(stage, stage_n, lane, ctrl, bin_items, capacity, true);
+    if (COUNT_STEPS) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { n_inner += __shfl_xor_sync(PT_FULL, n_inner, o); n_leaf += __shfl_xor_sync(PT_FULL, n_leaf, o); }
+        if (lane == 0) { atomicAdd(&step_counters[0], (unsigned long long)n_inner); atomicAdd(&step_counters[1], (unsigned long long)n_leaf); }
+    }
 }
 
 // ---- stage 2: shade / miss, binned by shader; survivors are compacted into the next ray queue ------------
@@ -300,7 +307,7 @@ __global__ void __launch_bounds__(128) k_shade(SceneDev sc, uint2 key, uint32_t 
                                                uint32_t capacity, BounceCtrl* __restrict__ ctrl,
                                                BounceCtrl* __restrict__ ctrl_next, float4* __restrict__ out_o,
                                                float4* __restrict__ out_d, float4* __restrict__ out_thr,
-                                               float4* __restrict__ path_out) {
+                                               float4* __restrict__ path_out, float4* __restrict__ gbuf_normal) {
     const uint32_t lane = threadIdx.x & 31u;
     // Work items are 32-item chunks of the five shader bins, so a warp never mixes shaders.  The output slot of
     // a hit item is a pure function of (bin, item): next queue = [diffuse | glossy | mix | glass] survivors in bin
@@ -351,6 +358,8 @@ __global__ void __launch_bounds__(128) k_shade(SceneDev sc, uint2 key, uint32_t 
                 const float3 c = thr * sky_radiance(sc.sky, d);
                 if (sc.has_emitters) { float4 p = path_out[pid]; path_out[pid] = make_float4(p.x + c.x, p.y + c.y, p.z + c.z, 0.f); }
                 else path_out[pid] = make_float4(c.x, c.y, c.z, 0.f);
+                // G-buffer of the display pipeline: a first-segment miss records -dir (path_tracer.cu:152)
+                if (gbuf_normal != nullptr && bounce == 0) gbuf_normal[pid] = make_float4(-d.x, -d.y, -d.z, 0.f);
                 continue;
             }
             const uint32_t prim = h.y >> 3;
@@ -359,6 +368,7 @@ __global__ void __launch_bounds__(128) k_shade(SceneDev sc, uint2 key, uint32_t 
             const MaterialRec m = sc.mats[mslot];
             float3 pos, normal;
             hit_attributes(g0, (int)(h.y & 7u), o, d, __uint_as_float(h.x), pos, normal);
+            if (gbuf_normal != nullptr && bounce == 0) gbuf_normal[pid] = make_float4(normal.x, normal.y, normal.z, 0.f);
             const float4 U = philox_uniform4(key, pixel, first_sample + s, 1u + (uint32_t)bounce);
             Scatter sct;
             shade_bin(bin, m, normal, d, U, sct);
@@ -413,6 +423,7 @@ __global__ void __launch_bounds__(256) k_accumulate(uint32_t npix, uint32_t n_sa
 
 // per-wave bookkeeping: rays traced = sum of the bounce input queues (diagnostic counter, 1 thread)
 __global__ void k_wave_stats(int max_depth, const BounceCtrl* __restrict__ ctrl, unsigned long long* __restrict__ segments) {
+    // segments[0] rays traced, [1] inner-node steps, [2] primitive tests (the latter two only with PT_OPT_COUNT_STEPS)
     unsigned long long n = 0;
     for (int b = 0; b < max_depth; ++b) n += ctrl[b].rays.v;
     *segments += n;

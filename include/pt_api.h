@@ -71,6 +71,8 @@ typedef struct pt_stats {
     uint32_t wave_paths;      /* paths in flight per wave                                     */
     uint32_t traverse_launches; /* closest-hit launches of the last pt_render_frame (= waves x depth) */
     uint32_t waves;           /* waves of the last pt_render_frame                            */
+    uint64_t node_steps;      /* inner BVH nodes visited (only with PT_OPT_COUNT_STEPS)       */
+    uint64_t prim_tests;      /* sphere / cylinder tests run (only with PT_OPT_COUNT_STEPS)   */
 } pt_stats;
 
 enum {
@@ -82,6 +84,7 @@ enum {
                                  BYTES per row (cuSrc/textures.cu:32); 0: upload whole rows         */
     PT_OPT_TRAV_REFILL_MIN = 5, /* tuning: idle lanes per warp that trigger a ray refill (1..32)     */
     PT_OPT_TRAV_STEPS = 6,      /* tuning: traversal rounds between two refill / retire checks       */
+    PT_OPT_COUNT_STEPS = 8,     /* 1: use the instrumented traversal kernel that counts node visits / primitive tests */
     PT_OPT_TRAV_INNER_RUN = 7   /* tuning: inner-node steps a lane may take before the warp regroups for leaf tests */
 };
 

@@ -635,6 +635,56 @@ void orc_segment_rays(int seg, int sample, int max_depth, unsigned long long see
             r[6] = ray.tmin; r[7] = ray.tmax;
         }
 }
+/* Denoising (cuSrc/path_tracer.cu:177-239) + Mix (cuSrc/path_tracer.cu:241-254) for one sample.
+ * color3 / normal3: SamplePixel's render_target and normal buffer (W*H*3); depth is constant (see
+ * pt_display.cuh) so p_w = exp(-0/pi) = 1.  mix3 is the running mean (in/out), idx the 1-based
+ * cur_sample_idx_.  `exp(-(dist2) / M_PI)` is a double exp; taps wrap across row ends exactly like the
+ * reference's `cur_off = v*width+u` bound check (:212-216).  bgra[4p+3] is never written by the reference;
+ * this restatement leaves it untouched too. */
+void orc_denoise_mix(int W, int H, const float* color3, const float* normal3, float* mix3, uint8_t* bgra, int idx) {
+    static const float kern[5][5] = {{1.f, 4.f, 7.f, 4.f, 1.f}, {4.f, 16.f, 26.f, 16.f, 4.f}, {7.f, 26.f, 41.f, 26.f, 7.f},
+                                     {4.f, 16.f, 26.f, 16.f, 4.f}, {1.f, 4.f, 7.f, 4.f, 1.f}};
+    std::vector<float> den((size_t)W * H * 3);
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            const int off = y * W + x;
+            V3 cval = v3(color3[3 * off], color3[3 * off + 1], color3[3 * off + 2]);
+            V3 nval = v3(normal3[3 * off], normal3[3 * off + 1], normal3[3 * off + 2]);
+            V3 sum = v3(0, 0, 0); float cum_w = 0.0f;
+            for (int i = 0; i < 5; ++i)
+                for (int j = 0; j < 5; ++j) {
+                    int u = x + (i - 2), v = y + (j - 2);
+                    int cur = v * W + u;
+                    float c_w, n_w, p_w; V3 ctmp;
+                    if (cur < 0 || cur >= W * H) { c_w = n_w = p_w = 0; ctmp = v3(0, 0, 0); }
+                    else {
+                        ctmp = v3(color3[3 * cur], color3[3 * cur + 1], color3[3 * cur + 2]);
+                        V3 t = sub(cval, ctmp);
+                        float dist2 = dot(t, t);
+                        c_w = (float)fmin(exp(-(double)dist2 / RT_PI), 1.0);
+                        t = sub(nval, v3(normal3[3 * cur], normal3[3 * cur + 1], normal3[3 * cur + 2]));
+                        dist2 = fmaxf(dot(t, t), 0.0f);
+                        n_w = (float)fmin(exp(-(double)dist2 / RT_PI), 1.0);
+                        p_w = 1.0f;
+                    }
+                    float weight = c_w * n_w * p_w;
+                    sum = add(sum, scale(ctmp, weight * kern[i][j]));
+                    cum_w += weight * kern[i][j];
+                }
+            V3 d = divs(sum, cum_w);
+            den[3 * off] = d.x; den[3 * off + 1] = d.y; den[3 * off + 2] = d.z;
+        }
+    const float t = 1.f / (float)idx;
+    for (int off = 0; off < W * H; ++off)
+        for (int k = 0; k < 3; ++k) {
+            float a = mix3[3 * off + k];
+            float b = fmaxf(0.f, fminf(den[3 * off + k], 1.f));                 /* clamp, helper_math.h:1168-1171 */
+            float m = a + t * (b - a);                                        /* lerp,  helper_math.h:1146-1149 */
+            mix3[3 * off + k] = m;
+            bgra[4 * off + (2 - k)] = (uint8_t)(255.99f * m);
+        }
+}
 int orc_sizeof(int) { return 0; }
 int orc_max_threads(void) { return omp_get_max_threads(); }
 }

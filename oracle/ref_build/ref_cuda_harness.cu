@@ -160,4 +160,24 @@ int refcuda_render(int w, int h, const float* origin, const float* look_at, floa
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     return 0;
 }
+/* The reference's own Denoising + Mix kernels (path_tracer.cu:177-254) on caller-supplied buffers.
+ * w, h must be multiples of 16 (the kernels derive the image size from the grid, :186-187). */
+int refcuda_denoise_mix(int w, int h, const float* color3, const float* normal3, float* mix3, uint8_t* bgra, int idx) {
+    if (w % 16 || h % 16) return -9;
+    size_t np = (size_t)w * h;
+    float3 *d_c, *d_n, *d_dn, *d_mix; float* d_depth; uint8_t* d_out;
+    cudaMalloc(&d_c, np * 12); cudaMalloc(&d_n, np * 12); cudaMalloc(&d_dn, np * 12); cudaMalloc(&d_mix, np * 12);
+    cudaMalloc(&d_depth, np * 4); cudaMalloc(&d_out, np * 4);
+    cudaMemcpy(d_c, color3, np * 12, cudaMemcpyHostToDevice); cudaMemcpy(d_n, normal3, np * 12, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_mix, mix3, np * 12, cudaMemcpyHostToDevice); cudaMemcpy(d_out, bgra, np * 4, cudaMemcpyHostToDevice);
+    std::vector<float> depth(np, DEFAULT_RAY_TMAX);
+    cudaMemcpy(d_depth, depth.data(), np * 4, cudaMemcpyHostToDevice);
+    dim3 tpb(16, 16), nb(w / 16, h / 16);
+    Denoising<<<nb, tpb>>>(d_c, d_n, d_depth, d_dn, 1.f);
+    Mix<<<nb, tpb>>>(d_dn, d_mix, d_out, idx);
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaMemcpy(mix3, d_mix, np * 12, cudaMemcpyDeviceToHost); cudaMemcpy(bgra, d_out, np * 4, cudaMemcpyDeviceToHost);
+    cudaFree(d_c); cudaFree(d_n); cudaFree(d_dn); cudaFree(d_mix); cudaFree(d_depth); cudaFree(d_out);
+    return e == cudaSuccess ? 0 : -1;
+}
 }

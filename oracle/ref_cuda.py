@@ -52,6 +52,15 @@ class RefCuda:
             raise RuntimeError(f"refcuda_trace failed: {rc}")
         return prim, t, nrm, pos
 
+    def denoise_mix(self, color: np.ndarray, normal: np.ndarray, mix: np.ndarray, bgra: np.ndarray, idx: int):
+        """The reference's own Denoising + Mix kernels, in place on `mix` ([H,W,3] f32) and `bgra` ([H,W,4] u8)."""
+        h, w = color.shape[:2]
+        color = np.ascontiguousarray(color, np.float32); normal = np.ascontiguousarray(normal, np.float32)
+        rc = self.lib.refcuda_denoise_mix(C.c_int(w), C.c_int(h), C.c_void_p(color.ctypes.data), C.c_void_p(normal.ctypes.data),
+                                          C.c_void_p(mix.ctypes.data), C.c_void_p(bgra.ctypes.data), C.c_int(idx))
+        if rc:
+            raise RuntimeError(f"refcuda_denoise_mix failed: {rc}")
+
     def render(self, cam, spp: int, warmup: int = 1, seed: int = 1234, want_image: bool = False):
         """Returns dict(kernel_ms, service_ms, traced_pixels, mpaths_kernel, mpaths_service[, sum_rgb])."""
         o = (C.c_float * 3)(*[float(v) for v in cam.origin]); a = (C.c_float * 3)(*[float(v) for v in cam.look_at])

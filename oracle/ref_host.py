@@ -178,6 +178,13 @@ class PortOracle(RefHost):
     def __init__(self, path: str = PORT_LIB_PATH):
         super().__init__(path, "orc_")
 
+    def denoise_mix(self, color: np.ndarray, normal: np.ndarray, mix: np.ndarray, bgra: np.ndarray, idx: int):
+        """Denoising + Mix of one sample, in place on `mix` ([H,W,3] f32) and `bgra` ([H,W,4] u8)."""
+        h, w = color.shape[:2]
+        color = np.ascontiguousarray(color, np.float32); normal = np.ascontiguousarray(normal, np.float32)
+        self.lib.ref_denoise_mix(C.c_int(w), C.c_int(h), _p(color, C.c_float), _p(normal, C.c_float), _p(mix, C.c_float),
+                                 _p(bgra, C.c_uint8), C.c_int(idx))
+
     def segment_rays(self, cam, seg: int, sample: int = 0, max_depth: int = 8, seed: int = 0):
         """Rays of path segment `seg` for every pixel: (rays8 [H*W,8], valid [H*W] bool)."""
         self.set_camera(cam)

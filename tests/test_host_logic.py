@@ -54,7 +54,7 @@ def test_product_does_not_touch_oracle():
 
 def test_struct_layouts_match_header():
     assert C.sizeof(api.PtMaterial) == 48 and C.sizeof(api.PtCamera) == 52
-    assert C.sizeof(api.PtStats) == 56
+    assert C.sizeof(api.PtStats) == 72
 
 
 def test_scene_generators_are_deterministic():
