@@ -42,7 +42,8 @@ EXPORTS = [
     "pt_add_cylinder", "pt_set_material", "pt_update_prim", "pt_set_sky_rgba8", "pt_build", "pt_render_frame",
     "pt_render_frame_async", "pt_synchronize", "pt_reset_accum", "pt_read_accum", "pt_accum_device_ptr",
     "pt_get_stats", "pt_dispatch_ray", "pt_texture_create_rgba8", "pt_texture_destroy", "pt_trace_rays",
-    "pt_shade_batch", "pt_raygen_batch", "pt_sky_lookup", "pt_philox_uniforms", "pt_camera_basis", "pt_last_error",
+    "pt_shade_batch", "pt_raygen_batch", "pt_sky_lookup", "pt_philox_uniforms", "pt_camera_basis", "pt_camera_control",
+    "pt_last_error",
     "pt_version",
 ]
 
@@ -85,6 +86,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.pt_sky_lookup.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.pt_philox_uniforms.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]
     lib.pt_camera_basis.argtypes = [C.POINTER(PtCamera), C.c_void_p]
+    lib.pt_camera_control.argtypes = [C.POINTER(PtCamera), C.c_int, C.c_float, C.c_float]
     lib.pt_accum_device_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     lib.pt_get_stats.argtypes = [C.c_void_p, C.POINTER(PtStats)]
     lib.pt_texture_create_rgba8.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
@@ -120,6 +122,21 @@ def camera_basis(cam) -> np.ndarray:
     if rc:
         raise PtError(load_library().pt_last_error().decode())
     return out
+
+
+CAM_LEFT, CAM_RIGHT, CAM_FORWARD, CAM_BACKWARD, CAM_UP, CAM_DOWN = 0, 1, 2, 3, 4, 5
+CAM_ROT_UP, CAM_ROT_DOWN, CAM_ROT_LEFT, CAM_ROT_RIGHT, CAM_SCALE_FOV = 6, 7, 8, 9, 10
+
+
+def camera_control(cam, op: int, arg: float, move_speed: float = 50.0):
+    """MotionalCamera::MoveEye* / RotateAround* / ScaleFov (motional_camera.cu:76-168) on a scenes.Camera, in place."""
+    c = to_pt_camera(cam)
+    if load_library().pt_camera_control(C.byref(c), int(op), float(arg), float(move_speed)):
+        raise PtError(load_library().pt_last_error().decode())
+    cam.origin = tuple(np.float32(v) for v in c.origin)
+    cam.look_at = tuple(np.float32(v) for v in c.look_at)
+    cam.view_fov = float(np.float32(c.view_fov_deg))
+    return cam
 
 
 class Renderer:

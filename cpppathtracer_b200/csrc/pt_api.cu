@@ -927,6 +927,36 @@ int pt_camera_basis(const pt_camera* cam, float out19[19]) {
     return PT_OK;
 }
 
+int pt_camera_control(pt_camera* cam, int op, float arg, float move_speed) {
+    if (!cam || op < 0 || op > 10) return fail(PT_ERR_INVALID, "bad camera control");
+    H3 o = h3(cam->origin[0], cam->origin[1], cam->origin[2]), a = h3(cam->look_at[0], cam->look_at[1], cam->look_at[2]);
+    const H3 vup = h3(cam->vup[0], cam->vup[1], cam->vup[2]);
+    auto neg = [](H3 v) { return h3(-v.x, -v.y, -v.z); };
+    if (op <= 3) {
+        // left = -normalize(cross(vup, w)), back = -normalize(cross(left, vup))   (motional_camera.cu:77-78,93-95)
+        const H3 w = hnormalize(hsub(o, a));
+        const H3 left = neg(hnormalize(hcross(vup, w)));
+        const H3 dir = op >= 2 ? neg(hnormalize(hcross(left, vup))) : left;
+        const H3 step = hscale(dir, arg * move_speed);
+        if (op == 0 || op == 3) { o = hadd(o, step); a = hadd(a, step); } else { o = hsub(o, step); a = hsub(a, step); }
+    } else if (op <= 5) {
+        const H3 step = hscale(vup, arg * move_speed);
+        if (op == 4) { o = hadd(o, step); a = hadd(a, step); } else { o = hsub(o, step); a = hsub(a, step); }
+    } else if (op <= 9) {
+        a = hadd(o, hnormalize(hsub(a, o)));
+        const H3 w = hnormalize(hsub(a, o));
+        const H3 left = hnormalize(hcross(vup, w));
+        const H3 axis = op <= 7 ? hnormalize(hcross(w, left)) : left;
+        a = (op == 6 || op == 8) ? hadd(a, hscale(axis, arg)) : hsub(a, hscale(axis, arg));
+        a = hadd(o, hnormalize(hsub(a, o)));
+    } else {
+        cam->view_fov_deg = (float)((double)cam->view_fov_deg + (double)arg * 3.14159265358979323846 / 180.0f);
+    }
+    cam->origin[0] = o.x; cam->origin[1] = o.y; cam->origin[2] = o.z;
+    cam->look_at[0] = a.x; cam->look_at[1] = a.y; cam->look_at[2] = a.z;
+    return PT_OK;
+}
+
 int pt_dispatch_ray(pt_scene* s, const pt_camera* cam, int max_depth, uint64_t seed, uint32_t sample_idx,
                     uint8_t* bgra_out, size_t nbytes) {
     return display_dispatch(s, cam, max_depth, seed, sample_idx, bgra_out, nbytes);

@@ -158,6 +158,12 @@ int pt_philox_uniforms(pt_scene* s, int n, uint64_t seed, const uint32_t* pixel_
 /* MotionalCamera::GetCopy basis (host math): out19 = u v w top_left horizontal vertical dist_to_focus */
 int pt_camera_basis(const pt_camera* cam, float out19[19]);
 
+/* MotionalCamera::MoveEye{Left,Right,Forward,Backward,Up,Down} / RotateAround{Up,Down,Left,Right} / ScaleFov
+ * (cuSrc/motional_camera.cu:76-168) applied to `cam` in place (host math, no device needed).
+ * op: 0 left, 1 right, 2 forward, 3 backward, 4 up, 5 down (arg = coefficient, move_speed), 6 rotate up,
+ * 7 rotate down, 8 rotate left, 9 rotate right (arg = delta), 10 scale fov (arg = d). */
+int pt_camera_control(pt_camera* cam, int op, float arg, float move_speed);
+
 const char* pt_last_error(void);
 const char* pt_version(void);
 

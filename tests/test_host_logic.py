@@ -100,3 +100,25 @@ def test_frame_round_robin():
 def test_mean_from_sum():
     s = np.zeros((2, 2, 4), np.float32); s[..., :3] = 8.0; s[..., 3] = 4.0
     assert np.array_equal(ptd.mean_from_sum(s), np.full((2, 2, 3), 2.0, np.float32))
+
+
+def test_camera_control_matches_reference_poses():
+    """pt_camera_control (host math in the library) vs the poses the reference's own MotionalCamera produced."""
+    from conftest import golden
+    g = golden("sky_camera.npz")
+    cam = scenes.Camera(16, 16, tuple(g["poses"][0][:3]), tuple(g["poses"][0][3:6]), view_fov=float(g["poses"][0][6]))
+    for (op, arg), want in zip(g["ops"], g["poses"][1:]):
+        api.camera_control(cam, int(op), float(np.float32(arg)))
+        got = np.array(list(cam.origin) + list(cam.look_at) + [cam.view_fov], np.float32)
+        assert np.array_equal(got, want)
+
+
+def test_video_camera_path_and_moving_objects():
+    from cpppathtracer_b200 import video
+    sc = scenes.sphere_field(100, 64, 36)
+    cams = video.camera_path(sc.camera, 5)
+    assert len(cams) == 5 and cams[0].origin == sc.camera.origin and cams[1].origin != cams[0].origin
+    ids, c = video.moving_spheres(sc, 3)
+    ids2, c2 = video.moving_spheres(sc, 4)
+    assert np.array_equal(ids, ids2) and len(ids) == 10 and not np.array_equal(c, c2)
+    assert (c[:, 1] >= sc.radius[ids] - 1e-6).all()
