@@ -118,7 +118,7 @@ def cpu_baseline_leg(sc, sky, budget_s: float = 15.0):
             "segments_per_path": st["segments"] / st["paths"]}
 
 
-def reference_arm(args):
+def reference_arm(args, out):
     """`--impl reference`: the reference's CPU implementation of the path, all host threads, rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -144,13 +144,13 @@ def reference_arm(args):
     dt = time.perf_counter() - t0
     v = paths / dt / 1e6
     sample = f"{sc.camera.width}x{sc.camera.height} x {spp} spp per step of the workload scene, depth 8"
-    print(json.dumps({
+    print(file=out, flush=True, *[json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": dict(WORKLOAD, sample=sample),
         "cpu_baseline": {"value": v, "unit": "Mpaths/s", "cores": cores, "kind": orc.kind, "sample": sample},
         "e2e": {"value": v, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0}))
+        "gpu_launches": 0})])
 
 
 def ref_cuda_leg(sc, sky):
@@ -170,7 +170,17 @@ def ref_cuda_leg(sc, sky):
         return {"unavailable": str(e)[:200]}
 
 
+def _quiet_stdout():
+    """Libraries (NCCL's version banner) write to fd 1; the driver wants exactly ONE JSON line there.
+    Point fd 1 at stderr for the duration of the run and return a file object on the real stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    real_stdout = _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -181,7 +191,7 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
-        reference_arm(args)
+        reference_arm(args, real_stdout)
         return
 
     import torch
@@ -318,7 +328,7 @@ def main():
             rc = ref_cuda_leg(sc, sky)
             if rc is not None:
                 line["ref_cuda_baseline"] = rc
-        print(json.dumps(line))
+        print(json.dumps(line), file=real_stdout, flush=True)
     r.close()
     if world > 1:
         dist.destroy_process_group()
