@@ -139,12 +139,23 @@ __device__ __forceinline__ void lane_begin(const SceneDev& sc, LaneRay& r, int* 
     r.node = sc.n_tree_prims > 0 ? 0 : PT_SENTINEL;
 }
 
+// One 64-byte node = two 256-bit loads (LDG.E.256, new on sm_100): half the LSU instructions and L1 wavefronts
+// of four 128-bit loads -- the walk is bound by the L1 wavefront pipe on incoherent bounces.
+__device__ __forceinline__ void load_node(const float4* __restrict__ nodes, int node, float4& n0, float4& n1, float4& n2,
+                                          float4& n3) {
+    const float4* p = nodes + 4 * (size_t)node;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(n0.x), "=f"(n0.y), "=f"(n0.z), "=f"(n0.w), "=f"(n1.x), "=f"(n1.y), "=f"(n1.z), "=f"(n1.w)
+                 : "l"(p));
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(n2.x), "=f"(n2.y), "=f"(n2.z), "=f"(n2.w), "=f"(n3.x), "=f"(n3.y), "=f"(n3.z), "=f"(n3.w)
+                 : "l"(p + 2));
+}
+
 __device__ __forceinline__ void lane_inner(const SceneDev& sc, LaneRay& r, int* stack) {
     {
-        const float4 n0 = __ldg(&sc.nodes[4 * r.node + 0]);
-        const float4 n1 = __ldg(&sc.nodes[4 * r.node + 1]);
-        const float4 n2 = __ldg(&sc.nodes[4 * r.node + 2]);
-        const float4 n3 = __ldg(&sc.nodes[4 * r.node + 3]);
+        float4 n0, n1, n2, n3;
+        load_node(sc.nodes, r.node, n0, n1, n2, n3);
         const float a0x = fmaf(n0.x, r.ix, -r.ox), a1x = fmaf(n0.y, r.ix, -r.ox);
         const float a0y = fmaf(n0.z, r.iy, -r.oy), a1y = fmaf(n0.w, r.iy, -r.oy);
         const float a0z = fmaf(n2.x, r.iz, -r.oz), a1z = fmaf(n2.y, r.iz, -r.oz);
