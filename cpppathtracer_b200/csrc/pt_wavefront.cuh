@@ -97,7 +97,12 @@ __global__ void __launch_bounds__(256) k_raygen(CameraFrame cam, uint2 key, uint
 // neighbours keep walking, so a warp no longer idles until its longest ray ends (v1: 12.7 of 32 lanes active
 // per instruction).  Finished rays are staged per warp in shared memory and binned by shader 32 at a time,
 // one atomic per warp and bin.
+#ifndef PT_TRAV_WARPS
 #define PT_TRAV_WARPS 4
+#endif
+#ifndef PT_TRAV_MIN_BLOCKS
+#define PT_TRAV_MIN_BLOCKS 1
+#endif
 #define PT_REFILL_MIN 32       // refill when at least this many lanes are idle (32: a warp refills as a whole;
                                // measured on C2: partial refills gain nothing, profiles/r01_v2_sweep.md)
 #define PT_STEPS_PER_CHECK 8   // traversal rounds between two refill / retire checks
@@ -222,7 +227,7 @@ __device__ __forceinline__ void flush_stage(uint32_t* stage, uint32_t& stage_n, 
 }
 
 template <bool PER_RAY_RANGE, bool COUNT_STEPS>
-__global__ void __launch_bounds__(32 * PT_TRAV_WARPS) k_traverse(SceneDev sc, const float4* __restrict__ ray_o,
+__global__ void __launch_bounds__(32 * PT_TRAV_WARPS, PT_TRAV_MIN_BLOCKS) k_traverse(SceneDev sc, const float4* __restrict__ ray_o,
                                                                 const float4* __restrict__ ray_d,
                                                                 const float2* __restrict__ ray_range, float tmin_all,
                                                                 BounceCtrl* __restrict__ ctrl, uint2* __restrict__ hit,
