@@ -95,7 +95,8 @@ struct pt_scene {
     // wave queues
     DevBuf<float4> q_o[2], q_d[2], q_thr[2], path_out;
     DevBuf<uint2> hit;
-    DevBuf<uint32_t> bin_items;
+    DevBuf<float4> hq_o, hq_d, hq_thr;
+    DevBuf<uint2> hq_hit;
     DevBuf<BounceCtrl> ctrl;
     DevBuf<unsigned long long> seg_counter;
     uint32_t capacity = 0;
@@ -367,7 +368,11 @@ int ensure_frame(pt_scene* s, int w, int h) {
 int ensure_queues(pt_scene* s, uint32_t cap, int max_depth) {
     if (cap > s->capacity) {
         for (int k = 0; k < 2; ++k) { CK(s->q_o[k].reserve(cap)); CK(s->q_d[k].reserve(cap)); CK(s->q_thr[k].reserve(cap)); }
-        CK(s->path_out.reserve(cap)); CK(s->hit.reserve(cap)); CK(s->bin_items.reserve((size_t)NUM_BINS * cap));
+        CK(s->path_out.reserve(cap)); CK(s->hit.reserve(cap));
+        // hit queues: the allocation is released first so that growing never holds two copies
+        s->hq_o.release(); s->hq_d.release(); s->hq_thr.release(); s->hq_hit.release();
+        CK(s->hq_o.reserve((size_t)NUM_BINS * cap)); CK(s->hq_d.reserve((size_t)NUM_BINS * cap));
+        CK(s->hq_thr.reserve((size_t)NUM_BINS * cap)); CK(s->hq_hit.reserve((size_t)NUM_BINS * cap));
         s->capacity = cap;
     }
     CK(s->ctrl.reserve((size_t)max_depth + 2));
@@ -402,6 +407,7 @@ int render_async(pt_scene* s, const pt_camera* cam, int spp, int max_depth, uint
     const CameraFrame frame = to_device_frame(cam);
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
     const SceneDev sd = scene_dev(s);
+    HitQueues hq; hq.o = s->hq_o.p; hq.d = s->hq_d.p; hq.thr = s->hq_thr.p; hq.hit = s->hq_hit.p; hq.capacity = s->capacity;
     const bool timing = s->opt_stage_timing != 0;
     size_t ev_i = 0;
     auto stage_event = [&]() -> cudaError_t {
@@ -425,17 +431,15 @@ int render_async(pt_scene* s, const pt_camera* cam, int spp, int max_depth, uint
             CK(stage_event());
             if (s->opt_count_steps)
                 k_traverse<false, true><<<s->grid_traverse, 32 * PT_TRAV_WARPS, 0, st>>>(
-                    sd, s->q_o[cur].p, s->q_d[cur].p, nullptr, b == 0 ? 0.f : PT_BOUNCE_TMIN, s->ctrl.p + b, s->hit.p,
-                    s->bin_items.p, s->capacity, (uint32_t)s->opt_refill_min, s->opt_steps_per_check, s->opt_inner_run,
+                    sd, s->q_o[cur].p, s->q_d[cur].p, s->q_thr[cur].p, nullptr, b == 0 ? 0.f : PT_BOUNCE_TMIN, s->ctrl.p + b,
+                    s->hit.p, hq, (uint32_t)s->opt_refill_min, s->opt_steps_per_check, s->opt_inner_run,
                     s->seg_counter.p + 1);
             else
                 k_traverse<false, false><<<s->grid_traverse, 32 * PT_TRAV_WARPS, 0, st>>>(
-                    sd, s->q_o[cur].p, s->q_d[cur].p, nullptr, b == 0 ? 0.f : PT_BOUNCE_TMIN, s->ctrl.p + b, s->hit.p,
-                    s->bin_items.p, s->capacity, (uint32_t)s->opt_refill_min, s->opt_steps_per_check, s->opt_inner_run,
-                    nullptr);
+                    sd, s->q_o[cur].p, s->q_d[cur].p, s->q_thr[cur].p, nullptr, b == 0 ? 0.f : PT_BOUNCE_TMIN, s->ctrl.p + b,
+                    s->hit.p, hq, (uint32_t)s->opt_refill_min, s->opt_steps_per_check, s->opt_inner_run, nullptr);
             CK(stage_event());
-            k_shade<<<s->grid_shade, 128, 0, st>>>(sd, key, npix, first_sample + s0, b, max_depth, s->q_o[cur].p,
-                                                   s->q_d[cur].p, s->q_thr[cur].p, s->hit.p, s->bin_items.p, s->capacity,
+            k_shade<<<s->grid_shade, 128, 0, st>>>(sd, key, npix, first_sample + s0, b, max_depth, hq,
                                                    s->ctrl.p + b, s->ctrl.p + b + 1, s->q_o[cur ^ 1].p, s->q_d[cur ^ 1].p,
                                                    s->q_thr[cur ^ 1].p, s->path_out.p, gbuf_normal);
             launches += 2;
@@ -648,7 +652,7 @@ void pt_scene_destroy(pt_scene* s) {
     s->bvh_prims.release(); s->parent_inner.release(); s->parent_leaf.release(); s->flags.release(); s->children.release();
     s->codes.release(); s->codes_sorted.release(); s->ids.release(); s->ids_sorted.release(); s->bounds6.release();
     s->orig_id.release(); s->cub_tmp.release(); s->accum.release(); s->read_tmp.release(); s->path_out.release(); s->hit.release();
-    s->bin_items.release(); s->ctrl.release(); s->seg_counter.release();
+    s->hq_o.release(); s->hq_d.release(); s->hq_thr.release(); s->hq_hit.release(); s->ctrl.release(); s->seg_counter.release();
     for (int k = 0; k < 2; ++k) { s->q_o[k].release(); s->q_d[k].release(); s->q_thr[k].release(); s->scratch_i[k].release(); }
     for (auto& b : s->scratch_f) b.release();
     s->disp_color.release(); s->disp_normal.release(); s->disp_mix.release(); s->disp_depth.release(); s->disp_bgra.release();
@@ -816,11 +820,12 @@ int pt_trace_rays(pt_scene* s, int n, const float* rays8, int32_t* prim, float* 
     CK(s->scratch_f[1].reserve((size_t)2 * n)); CK(s->scratch_f[2].reserve(n)); CK(s->scratch_f[3].reserve((size_t)3 * n));
     CK(s->scratch_f[4].reserve((size_t)3 * n)); CK(s->scratch_i[0].reserve(n));
     CK(cudaMemsetAsync(s->ctrl.p, 0, 2 * sizeof(BounceCtrl), st));
+    HitQueues hq; hq.o = s->hq_o.p; hq.d = s->hq_d.p; hq.thr = s->hq_thr.p; hq.hit = s->hq_hit.p; hq.capacity = s->capacity;
     const int g = (n + 255) / 256;
     k_pack_rays<<<g, 256, 0, st>>>(n, s->scratch_f[0].p, s->q_o[0].p, s->q_d[0].p, (float2*)s->scratch_f[1].p, s->ctrl.p);
     k_traverse<true, false><<<s->grid_traverse, 32 * PT_TRAV_WARPS, 0, st>>>(
-        scene_dev(s), s->q_o[0].p, s->q_d[0].p, (const float2*)s->scratch_f[1].p, 0.f, s->ctrl.p, s->hit.p, s->bin_items.p,
-        s->capacity, (uint32_t)s->opt_refill_min, s->opt_steps_per_check, s->opt_inner_run, nullptr);
+        scene_dev(s), s->q_o[0].p, s->q_d[0].p, s->q_thr[0].p, (const float2*)s->scratch_f[1].p, 0.f, s->ctrl.p, s->hit.p, hq,
+        (uint32_t)s->opt_refill_min, s->opt_steps_per_check, s->opt_inner_run, nullptr);
     k_unpack_hits<<<g, 256, 0, st>>>(n, scene_dev(s), s->q_o[0].p, s->q_d[0].p, s->hit.p, s->scratch_i[0].p,
                                      s->scratch_f[2].p, s->scratch_f[3].p, s->scratch_f[4].p);
     s->stats.launches += 3;

@@ -54,7 +54,8 @@ struct WaveQueues {
     float4* ray_d[2];
     float4* thr[2];
     uint2* hit;
-    uint32_t* bin_items;      // NUM_BINS x capacity slot indices
+    // hit queues, one per shader bin (NUM_BINS x capacity each): the complete shading input of a finished ray
+    float4* hq_o; float4* hq_d; float4* hq_thr; uint2* hq_hit;
     float4* path_out;         // per path of the wave: radiance (rgb, -)
     BounceCtrl* ctrl;         // [max_depth + 1]
     uint32_t capacity;
@@ -198,13 +199,29 @@ __device__ __forceinline__ void lane_leaf(const SceneDev& sc, LaneRay& r, int* s
     }
 }
 
-// bin the staged (bin<<29 | slot) entries of this warp, 32 at a time
-__device__ __forceinline__ void flush_stage(uint32_t* stage, uint32_t& stage_n, uint32_t lane, BounceCtrl* ctrl,
-                                            uint32_t* __restrict__ bin_items, uint32_t capacity, bool everything) {
+// The hit queues: what a finished ray hands to the shade stage, one queue per shader bin, SoA float4:
+//   hq_o = (origin, bits pixel)  hq_d = (dir, bits sample)  hq_thr = (throughput)  hq_hit = (bits t, prim<<3|part)
+// The traversal warp that finished the rays also MOVES their records there (32 at a time, positions from one
+// atomic per warp and bin), so the shade stage streams its bin in order instead of gathering 16-byte pieces
+// through an index list (v3: 2x read amplification and a dependent DRAM round trip in k_shade).  The copy rides on
+// the memory system the ALU/L1-bound walk leaves idle (k_traverse used 2-7 % of DRAM bandwidth).
+struct HitQueues {
+    float4* o; float4* d; float4* thr; uint2* hit;
+    uint32_t capacity;     // entries per bin
+};
+struct StageEntry { uint32_t slot_bin; uint32_t t; uint32_t code; };   // slot_bin = bin<<29 | slot
+
+__device__ __forceinline__ void flush_stage(StageEntry* stage, uint32_t& stage_n, uint32_t lane, BounceCtrl* ctrl,
+                                            const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
+                                            const float4* __restrict__ thr, const HitQueues& hq, bool everything) {
     while (stage_n >= 32u || (everything && stage_n > 0u)) {
         const uint32_t cnt = stage_n < 32u ? stage_n : 32u;
-        const uint32_t e = lane < cnt ? stage[lane] : 0xFFFFFFFFu;
-        const int bin = lane < cnt ? (int)(e >> 29) : -1;
+        StageEntry e; e.slot_bin = 0xFFFFFFFFu; e.t = 0u; e.code = 0u;
+        if (lane < cnt) e = stage[lane];
+        const int bin = lane < cnt ? (int)(e.slot_bin >> 29) : -1;
+        const uint32_t slot = e.slot_bin & 0x1FFFFFFFu;
+        float4 o4 = make_float4(0, 0, 0, 0), d4 = o4, t4 = o4;
+        if (lane < cnt) { o4 = ray_o[slot]; d4 = ray_d[slot]; t4 = thr[slot]; }
 #pragma unroll
         for (int b = 0; b < NUM_BINS; ++b) {
             const uint32_t m = __ballot_sync(PT_FULL, bin == b);
@@ -213,12 +230,16 @@ __device__ __forceinline__ void flush_stage(uint32_t* stage, uint32_t& stage_n, 
                 const int leader = __ffs(m) - 1;
                 if ((int)lane == leader) off = atomicAdd(&ctrl->bin_count[b].v, (uint32_t)__popc(m));
                 off = __shfl_sync(PT_FULL, off, leader);
-                if (bin == b) bin_items[(size_t)b * capacity + off + __popc(m & ((1u << lane) - 1u))] = e & 0x1FFFFFFFu;
+                if (bin == b) {
+                    const size_t j = (size_t)b * hq.capacity + off + __popc(m & ((1u << lane) - 1u));
+                    hq.o[j] = o4; hq.d[j] = d4; hq.thr[j] = t4; hq.hit[j] = make_uint2(e.t, e.code);
+                }
             }
         }
         __syncwarp();
         const uint32_t rest = stage_n - cnt;
-        const uint32_t moved = lane < rest ? stage[32u + lane] : 0u;
+        StageEntry moved; moved.slot_bin = 0u; moved.t = 0u; moved.code = 0u;
+        if (lane < rest) moved = stage[32u + lane];
         __syncwarp();
         if (lane < rest) stage[lane] = moved;
         stage_n = rest;
@@ -229,14 +250,15 @@ __device__ __forceinline__ void flush_stage(uint32_t* stage, uint32_t& stage_n, 
 template <bool PER_RAY_RANGE, bool COUNT_STEPS>
 __global__ void __launch_bounds__(32 * PT_TRAV_WARPS, PT_TRAV_MIN_BLOCKS) k_traverse(SceneDev sc, const float4* __restrict__ ray_o,
                                                                 const float4* __restrict__ ray_d,
+                                                                const float4* __restrict__ ray_thr,
                                                                 const float2* __restrict__ ray_range, float tmin_all,
-                                                                BounceCtrl* __restrict__ ctrl, uint2* __restrict__ hit,
-                                                                uint32_t* __restrict__ bin_items, uint32_t capacity,
-                                                                uint32_t refill_min, int steps_per_check, int inner_run,
+                                                                BounceCtrl* __restrict__ ctrl, uint2* __restrict__ slot_hit,
+                                                                HitQueues hq, uint32_t refill_min, int steps_per_check,
+                                                                int inner_run,
                                                                 unsigned long long* __restrict__ step_counters) {
-    __shared__ uint32_t s_stage[PT_TRAV_WARPS][64];
+    __shared__ StageEntry s_stage[PT_TRAV_WARPS][64];
     const uint32_t lane = threadIdx.x & 31u;
-    uint32_t* stage = s_stage[threadIdx.x >> 5];
+    StageEntry* stage = s_stage[threadIdx.x >> 5];
     uint32_t stage_n = 0;
     const uint32_t n = ctrl->in_count.v;
     int stack[PT_STACK];
@@ -293,19 +315,21 @@ __global__ void __launch_bounds__(32 * PT_TRAV_WARPS, PT_TRAV_MIN_BLOCKS) k_trav
         const uint32_t fm = __ballot_sync(PT_FULL, fin);
         if (fm) {
             if (fin) {
-                hit[r.slot] = make_uint2(__float_as_uint(r.best_t), r.best_code);
+                // the parity entry point (pt_trace_rays) reads results by ray slot; the render path does not
+                if (PER_RAY_RANGE) slot_hit[r.slot] = make_uint2(__float_as_uint(r.best_t), r.best_code);
                 const uint32_t bin = (r.best_code == PT_MISS_CODE)
                                          ? (uint32_t)BIN_MISS
                                          : (__float_as_uint(__ldg(&sc.geo1[r.best_code >> 3]).w) >> 28);
-                stage[stage_n + __popc(fm & ((1u << lane) - 1u))] = (bin << 29) | r.slot;
+                StageEntry e; e.slot_bin = (bin << 29) | r.slot; e.t = __float_as_uint(r.best_t); e.code = r.best_code;
+                stage[stage_n + __popc(fm & ((1u << lane) - 1u))] = e;
                 active = false;
             }
             stage_n += (uint32_t)__popc(fm);
             __syncwarp();
-            flush_stage(stage, stage_n, lane, ctrl, bin_items, capacity, false);
+            flush_stage(stage, stage_n, lane, ctrl, ray_o, ray_d, ray_thr, hq, false);
         }
     }
-    flush_stage(stage, stage_n, lane, ctrl, bin_items, capacity, true);
+    flush_stage(stage, stage_n, lane, ctrl, ray_o, ray_d, ray_thr, hq, true);
     if (COUNT_STEPS) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { n_inner += __shfl_xor_sync(PT_FULL, n_inner, o); n_leaf += __shfl_xor_sync(PT_FULL, n_leaf, o); }
@@ -317,10 +341,7 @@ __global__ void __launch_bounds__(32 * PT_TRAV_WARPS, PT_TRAV_MIN_BLOCKS) k_trav
 // Replaces Object::ClosetHit -> Material::EvalAttenuationAndCreateRay (object.cu:130-132, material.cu:145-163),
 // Miss (path_tracer.cu:117-122) and the per-segment bookkeeping of SamplePixel (path_tracer.cu:156-170).
 __global__ void __launch_bounds__(128) k_shade(SceneDev sc, uint2 key, uint32_t npix, uint32_t first_sample,
-                                               int bounce, int max_depth, const float4* __restrict__ ray_o,
-                                               const float4* __restrict__ ray_d, const float4* __restrict__ thr_in,
-                                               const uint2* __restrict__ hit, const uint32_t* __restrict__ bin_items,
-                                               uint32_t capacity, BounceCtrl* __restrict__ ctrl,
+                                               int bounce, int max_depth, HitQueues hq, BounceCtrl* __restrict__ ctrl,
                                                BounceCtrl* __restrict__ ctrl_next, float4* __restrict__ out_o,
                                                float4* __restrict__ out_d, float4* __restrict__ out_thr,
                                                float4* __restrict__ path_out, float4* __restrict__ gbuf_normal) {
@@ -360,11 +381,11 @@ __global__ void __launch_bounds__(128) k_shade(SceneDev sc, uint2 key, uint32_t 
             const uint32_t item = ((chunk - first_chunk) << 5) + lane;
             const bool valid = item < n_bin;
             if (!valid) continue;
-            const uint32_t slot = bin_items[(size_t)bin * capacity + item];
-            const float4 o4 = ray_o[slot];
-            const float4 d4 = ray_d[slot];
-            const float4 t4 = thr_in[slot];
-            const uint2 h = hit[slot];
+            const size_t q = (size_t)bin * hq.capacity + item;
+            const float4 o4 = hq.o[q];
+            const float4 d4 = hq.d[q];
+            const float4 t4 = hq.thr[q];
+            const uint2 h = hq.hit[q];
             const uint32_t pixel = __float_as_uint(o4.w);
             const uint32_t s = __float_as_uint(d4.w);
             const size_t pid = (size_t)s * npix + pixel;
