@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpt_b200.so")
 
 PT_OPT_WAVE_PATHS, PT_OPT_STAGE_TIMING, PT_OPT_TIE_ORDER, PT_OPT_SKY_QUARTER_ROWS = 1, 2, 3, 4
-PT_OPT_TRAV_REFILL_MIN, PT_OPT_TRAV_STEPS, PT_OPT_TRAV_INNER_RUN, PT_OPT_COUNT_STEPS = 5, 6, 7, 8
+PT_OPT_TRAV_INNER_RUN, PT_OPT_COUNT_STEPS = 7, 8
 
 
 class PtMaterial(C.Structure):

@@ -76,7 +76,7 @@ struct pt_scene {
     int opt_tie_order = 1;
     int opt_sky_quarter = 1;
     int opt_count_steps = 0;
-    int opt_refill_min = PT_REFILL_MIN, opt_steps_per_check = PT_STEPS_PER_CHECK, opt_inner_run = 4;
+    int opt_inner_run = 4;
     // device scene
     DevBuf<float4> geo0, geo1, nodes, leaf_mn, leaf_mx, inner_mn, inner_mx;
     DevBuf<MaterialRec> mats;
@@ -93,10 +93,11 @@ struct pt_scene {
     int width = 0, height = 0;
     DevBuf<float4> accum;
     // wave queues
-    DevBuf<float4> q_o[2], q_d[2], q_thr[2], path_out;
-    DevBuf<uint2> hit;
-    DevBuf<float4> hq_o, hq_d, hq_thr;
-    DevBuf<uint2> hq_hit;
+    DevBuf<float4> path_out;
+    DevBuf<float4> hq_o[2], hq_d[2], hq_thr[2];   // hit queues, double-buffered over segments
+    DevBuf<uint2> hq_hit[2];
+    DevBuf<float4> q_o, q_d;                      // parity path only: the caller's ray batch
+    DevBuf<uint2> hit;                            // parity path only: results by ray slot
     DevBuf<BounceCtrl> ctrl;
     DevBuf<unsigned long long> seg_counter;
     uint32_t capacity = 0;
@@ -112,7 +113,7 @@ struct pt_scene {
     pt_stats stats{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> stage_events;
-    int grid_traverse = 0, grid_shade = 0;
+    int grid_bounce = 0;
     int last_depth = 0;
     size_t stage_events_used = 0;
     bool frame_recorded = false;
@@ -367,27 +368,38 @@ int ensure_frame(pt_scene* s, int w, int h) {
 
 int ensure_queues(pt_scene* s, uint32_t cap, int max_depth) {
     if (cap > s->capacity) {
-        for (int k = 0; k < 2; ++k) { CK(s->q_o[k].reserve(cap)); CK(s->q_d[k].reserve(cap)); CK(s->q_thr[k].reserve(cap)); }
-        CK(s->path_out.reserve(cap)); CK(s->hit.reserve(cap));
-        // hit queues: the allocation is released first so that growing never holds two copies
-        s->hq_o.release(); s->hq_d.release(); s->hq_thr.release(); s->hq_hit.release();
-        CK(s->hq_o.reserve((size_t)NUM_BINS * cap)); CK(s->hq_d.reserve((size_t)NUM_BINS * cap));
-        CK(s->hq_thr.reserve((size_t)NUM_BINS * cap)); CK(s->hq_hit.reserve((size_t)NUM_BINS * cap));
+        // released first so that growing never holds two copies
+        s->path_out.release();
+        for (int k = 0; k < 2; ++k) { s->hq_o[k].release(); s->hq_d[k].release(); s->hq_thr[k].release(); s->hq_hit[k].release(); }
+        CK(s->path_out.reserve(cap));
+        for (int k = 0; k < 2; ++k) {
+            CK(s->hq_o[k].reserve((size_t)NUM_BINS * cap)); CK(s->hq_d[k].reserve((size_t)NUM_BINS * cap));
+            CK(s->hq_thr[k].reserve((size_t)NUM_BINS * cap)); CK(s->hq_hit[k].reserve((size_t)NUM_BINS * cap));
+        }
         s->capacity = cap;
     }
-    CK(s->ctrl.reserve((size_t)max_depth + 2));
+    CK(s->ctrl.reserve((size_t)max_depth + 3));
     CK(s->seg_counter.reserve(4));
     return PT_OK;
 }
 
+HitQueues hit_queues(pt_scene* s, int k) {
+    HitQueues hq; hq.o = s->hq_o[k].p; hq.d = s->hq_d[k].p; hq.thr = s->hq_thr[k].p; hq.hit = s->hq_hit[k].p; hq.capacity = s->capacity;
+    return hq;
+}
+
 int launch_config(pt_scene* s) {
-    if (s->grid_traverse) return PT_OK;
-    int occ_t = 0, occ_s = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, k_traverse<false, false>, 32 * PT_TRAV_WARPS, 0));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_shade, 128, 0));
-    s->grid_traverse = s->sm_count * std::max(occ_t, 1);
-    s->grid_shade = s->sm_count * std::max(occ_s, 1);
+    if (s->grid_bounce) return PT_OK;
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bounce<SRC_HITS, false>, 32 * PT_BOUNCE_WARPS, 0));
+    s->grid_bounce = s->sm_count * std::max(occ, 1);
     return PT_OK;
+}
+
+template <int SRC>
+void launch_bounce(pt_scene* s, const BounceArgs& a, cudaStream_t st) {
+    if (s->opt_count_steps) k_bounce<SRC, true><<<s->grid_bounce, 32 * PT_BOUNCE_WARPS, 0, st>>>(a);
+    else k_bounce<SRC, false><<<s->grid_bounce, 32 * PT_BOUNCE_WARPS, 0, st>>>(a);
 }
 
 int render_async(pt_scene* s, const pt_camera* cam, int spp, int max_depth, uint64_t seed, uint32_t first_sample,
@@ -406,8 +418,10 @@ int render_async(pt_scene* s, const pt_camera* cam, int spp, int max_depth, uint
     cudaStream_t st = s->stream;
     const CameraFrame frame = to_device_frame(cam);
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
-    const SceneDev sd = scene_dev(s);
-    HitQueues hq; hq.o = s->hq_o.p; hq.d = s->hq_d.p; hq.thr = s->hq_thr.p; hq.hit = s->hq_hit.p; hq.capacity = s->capacity;
+    BounceArgs args;
+    memset(&args, 0, sizeof(args));
+    args.sc = scene_dev(s); args.key = key; args.npix = npix; args.max_depth = max_depth; args.inner_run = s->opt_inner_run;
+    args.cam = frame; args.path_out = s->path_out.p; args.gbuf_normal = gbuf_normal; args.step_counters = s->seg_counter.p + 1;
     const bool timing = s->opt_stage_timing != 0;
     size_t ev_i = 0;
     auto stage_event = [&]() -> cudaError_t {
@@ -418,34 +432,27 @@ int render_async(pt_scene* s, const pt_camera* cam, int spp, int max_depth, uint
     CK(cudaMemsetAsync(s->seg_counter.p, 0, 4 * sizeof(unsigned long long), st));
     CK(cudaEventRecord(s->ev0, st));
     uint64_t launches = 0;
+    BounceCtrl* const ctrl = s->ctrl.p;
+    BounceCtrl* const ctrl_cam = s->ctrl.p + max_depth + 1;     // work counter of the camera launch
     for (uint32_t s0 = 0; s0 < (uint32_t)spp; s0 += spp_per_wave) {
         const uint32_t ns = std::min<uint32_t>(spp_per_wave, (uint32_t)spp - s0);
         const uint32_t n_paths = npix * ns;
         CK(cudaMemsetAsync(s->ctrl.p, 0, ((size_t)max_depth + 2) * sizeof(BounceCtrl), st));
-        const int rg_grid = (int)std::min<uint32_t>((n_paths + 255u) / 256u, (uint32_t)s->sm_count * 16u);
-        k_raygen<<<rg_grid, 256, 0, st>>>(frame, key, npix, n_paths, first_sample + s0, s->q_o[0].p, s->q_d[0].p,
-                                          s->q_thr[0].p, s->path_out.p, s->has_emitters, s->ctrl.p);
-        ++launches;
-        int cur = 0;
-        for (int b = 0; b < max_depth; ++b) {
+        args.first_sample = first_sample + s0; args.n_paths = n_paths;
+        // segment 0: camera rays -> hit queue 0
+        CK(stage_event());
+        args.segment = 0; args.trace = 1; args.ctrl_in = ctrl_cam; args.ctrl_out = ctrl + 0; args.hq_out = hit_queues(s, 0);
+        launch_bounce<SRC_CAMERA>(s, args, st);
+        // segment k: shade the hits of segment k-1, trace the survivors; k == max_depth only shades
+        for (int k = 1; k <= max_depth; ++k) {
             CK(stage_event());
-            if (s->opt_count_steps)
-                k_traverse<false, true><<<s->grid_traverse, 32 * PT_TRAV_WARPS, 0, st>>>(
-                    sd, s->q_o[cur].p, s->q_d[cur].p, s->q_thr[cur].p, nullptr, b == 0 ? 0.f : PT_BOUNCE_TMIN, s->ctrl.p + b,
-                    s->hit.p, hq, (uint32_t)s->opt_refill_min, s->opt_steps_per_check, s->opt_inner_run,
-                    s->seg_counter.p + 1);
-            else
-                k_traverse<false, false><<<s->grid_traverse, 32 * PT_TRAV_WARPS, 0, st>>>(
-                    sd, s->q_o[cur].p, s->q_d[cur].p, s->q_thr[cur].p, nullptr, b == 0 ? 0.f : PT_BOUNCE_TMIN, s->ctrl.p + b,
-                    s->hit.p, hq, (uint32_t)s->opt_refill_min, s->opt_steps_per_check, s->opt_inner_run, nullptr);
-            CK(stage_event());
-            k_shade<<<s->grid_shade, 128, 0, st>>>(sd, key, npix, first_sample + s0, b, max_depth, hq,
-                                                   s->ctrl.p + b, s->ctrl.p + b + 1, s->q_o[cur ^ 1].p, s->q_d[cur ^ 1].p,
-                                                   s->q_thr[cur ^ 1].p, s->path_out.p, gbuf_normal);
-            launches += 2;
-            cur ^= 1;
+            args.segment = k; args.trace = k < max_depth ? 1 : 0;
+            args.ctrl_in = ctrl + (k - 1); args.ctrl_out = ctrl + k;
+            args.hq_in = hit_queues(s, (k - 1) & 1); args.hq_out = hit_queues(s, k & 1);
+            launch_bounce<SRC_HITS>(s, args, st);
         }
         CK(stage_event());
+        launches += (uint64_t)max_depth + 1;
         const int ac_grid = (int)std::min<uint32_t>((npix + 255u) / 256u, (uint32_t)s->sm_count * 8u);
         if (accumulate) k_accumulate<<<ac_grid, 256, 0, st>>>(npix, ns, s->path_out.p, s->accum.p);
         k_wave_stats<<<1, 1, 0, st>>>(max_depth, s->ctrl.p, s->seg_counter.p);
@@ -459,7 +466,7 @@ int render_async(pt_scene* s, const pt_camera* cam, int spp, int max_depth, uint
     s->stats.wave_paths = cap;
     s->stats.segments = 0;
     s->stats.waves = (uint32_t)(((uint32_t)spp + spp_per_wave - 1) / spp_per_wave);
-    s->stats.traverse_launches = s->stats.waves * (uint32_t)max_depth;
+    s->stats.traverse_launches = s->stats.waves * (uint32_t)max_depth;   // launches that trace (camera + max_depth-1 bounce)
     return PT_OK;
 }
 
@@ -472,17 +479,18 @@ int finish_frame(pt_scene* s, int max_depth_hint) {
     CK(cudaEventElapsedTime(&s->stats.render_ms, s->ev0, s->ev1));
     s->stats.segments = seg4[0]; s->stats.node_steps = seg4[1]; s->stats.prim_tests = seg4[2];
     if (s->opt_stage_timing && s->stage_events.size() >= 2) {
-        // events alternate: [traverse start, shade start] per bounce, then accumulate start, per wave
-        float trav = 0.f, shade = 0.f;
-        const size_t per_wave = 2 * (size_t)s->last_depth + 1;
+        // per wave: one event before each of the max_depth+1 k_bounce launches and one after the last.
+        // traverse_ms = launches that trace (segments 0 .. max_depth-1; they also shade the previous segment's hits),
+        // shade_ms = the final shade-only launch
+        float trace_ms = 0.f, tail_ms = 0.f;
+        const size_t per_wave = (size_t)s->last_depth + 2;
         for (size_t w0 = 0; w0 + per_wave <= s->stage_events_used; w0 += per_wave)
-            for (int b = 0; b < s->last_depth; ++b) {
-                float a = 0.f, bms = 0.f;
-                cudaEventElapsedTime(&a, s->stage_events[w0 + 2 * b], s->stage_events[w0 + 2 * b + 1]);
-                cudaEventElapsedTime(&bms, s->stage_events[w0 + 2 * b + 1], s->stage_events[w0 + 2 * b + 2]);
-                trav += a; shade += bms;
+            for (int k = 0; k <= s->last_depth; ++k) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, s->stage_events[w0 + k], s->stage_events[w0 + k + 1]);
+                if (k < s->last_depth) trace_ms += ms; else tail_ms += ms;
             }
-        s->stats.traverse_ms = trav; s->stats.shade_ms = shade;
+        s->stats.traverse_ms = trace_ms; s->stats.shade_ms = tail_ms;
     }
     return PT_OK;
 }
@@ -652,8 +660,8 @@ void pt_scene_destroy(pt_scene* s) {
     s->bvh_prims.release(); s->parent_inner.release(); s->parent_leaf.release(); s->flags.release(); s->children.release();
     s->codes.release(); s->codes_sorted.release(); s->ids.release(); s->ids_sorted.release(); s->bounds6.release();
     s->orig_id.release(); s->cub_tmp.release(); s->accum.release(); s->read_tmp.release(); s->path_out.release(); s->hit.release();
-    s->hq_o.release(); s->hq_d.release(); s->hq_thr.release(); s->hq_hit.release(); s->ctrl.release(); s->seg_counter.release();
-    for (int k = 0; k < 2; ++k) { s->q_o[k].release(); s->q_d[k].release(); s->q_thr[k].release(); s->scratch_i[k].release(); }
+    s->ctrl.release(); s->q_o.release(); s->q_d.release(); s->seg_counter.release();
+    for (int k = 0; k < 2; ++k) { s->hq_o[k].release(); s->hq_d[k].release(); s->hq_thr[k].release(); s->hq_hit[k].release(); s->scratch_i[k].release(); }
     for (auto& b : s->scratch_f) b.release();
     s->disp_color.release(); s->disp_normal.release(); s->disp_mix.release(); s->disp_depth.release(); s->disp_bgra.release();
     if (s->ev0) cudaEventDestroy(s->ev0);
@@ -671,16 +679,10 @@ int pt_set_option(pt_scene* s, int option, int64_t value) {
         case PT_OPT_STAGE_TIMING: s->opt_stage_timing = value != 0; return PT_OK;
         case PT_OPT_TIE_ORDER: s->opt_tie_order = value != 0; s->dirty = true; return PT_OK;
         case PT_OPT_SKY_QUARTER_ROWS: s->opt_sky_quarter = value != 0; return PT_OK;
-        case PT_OPT_TRAV_REFILL_MIN:
-            if (value < 1 || value > 32) return fail(PT_ERR_INVALID, "refill_min must be 1..32");
-            s->opt_refill_min = (int)value; return PT_OK;
         case PT_OPT_COUNT_STEPS: s->opt_count_steps = value != 0; return PT_OK;
         case PT_OPT_TRAV_INNER_RUN:
             if (value < 1 || value > 1024) return fail(PT_ERR_INVALID, "inner_run must be 1..1024");
             s->opt_inner_run = (int)value; return PT_OK;
-        case PT_OPT_TRAV_STEPS:
-            if (value < 1 || value > 1024) return fail(PT_ERR_INVALID, "steps must be 1..1024");
-            s->opt_steps_per_check = (int)value; return PT_OK;
         default: return fail(PT_ERR_INVALID, "unknown option");
     }
 }
@@ -812,21 +814,25 @@ int pt_trace_rays(pt_scene* s, int n, const float* rays8, int32_t* prim, float* 
     if (!s || !rays8 || n < 0) return fail(PT_ERR_INVALID, "bad argument");
     if (!s->built || s->dirty) return fail(PT_ERR_NOT_BUILT, "pt_build must be called after the scene changed");
     if (n == 0) return PT_OK;
-    int rc = ensure_queues(s, (uint32_t)n, 1); if (rc) return rc;
-    rc = ensure_sky(s); if (rc) return rc;
+    int rc = ensure_sky(s); if (rc) return rc;
     rc = launch_config(s); if (rc) return rc;
     cudaStream_t st = s->stream;
     rc = to_device(s->scratch_f[0], rays8, (size_t)8 * n, st); if (rc) return rc;
+    CK(s->q_o.reserve(n)); CK(s->q_d.reserve(n)); CK(s->hit.reserve(n)); CK(s->ctrl.reserve(4)); CK(s->seg_counter.reserve(4));
     CK(s->scratch_f[1].reserve((size_t)2 * n)); CK(s->scratch_f[2].reserve(n)); CK(s->scratch_f[3].reserve((size_t)3 * n));
     CK(s->scratch_f[4].reserve((size_t)3 * n)); CK(s->scratch_i[0].reserve(n));
     CK(cudaMemsetAsync(s->ctrl.p, 0, 2 * sizeof(BounceCtrl), st));
-    HitQueues hq; hq.o = s->hq_o.p; hq.d = s->hq_d.p; hq.thr = s->hq_thr.p; hq.hit = s->hq_hit.p; hq.capacity = s->capacity;
     const int g = (n + 255) / 256;
-    k_pack_rays<<<g, 256, 0, st>>>(n, s->scratch_f[0].p, s->q_o[0].p, s->q_d[0].p, (float2*)s->scratch_f[1].p, s->ctrl.p);
-    k_traverse<true, false><<<s->grid_traverse, 32 * PT_TRAV_WARPS, 0, st>>>(
-        scene_dev(s), s->q_o[0].p, s->q_d[0].p, s->q_thr[0].p, (const float2*)s->scratch_f[1].p, 0.f, s->ctrl.p, s->hit.p, hq,
-        (uint32_t)s->opt_refill_min, s->opt_steps_per_check, s->opt_inner_run, nullptr);
-    k_unpack_hits<<<g, 256, 0, st>>>(n, scene_dev(s), s->q_o[0].p, s->q_d[0].p, s->hit.p, s->scratch_i[0].p,
+    k_pack_rays<<<g, 256, 0, st>>>(n, s->scratch_f[0].p, s->q_o.p, s->q_d.p, (float2*)s->scratch_f[1].p, s->ctrl.p);
+    // the SAME bounce kernel as the render path, fed from the caller's batch (SRC_RAYS) instead of a shader
+    BounceArgs args;
+    memset(&args, 0, sizeof(args));
+    args.sc = scene_dev(s); args.segment = 0; args.max_depth = 1; args.trace = 1; args.inner_run = s->opt_inner_run;
+    args.ctrl_in = s->ctrl.p; args.ctrl_out = s->ctrl.p + 1;
+    args.ray_o = s->q_o.p; args.ray_d = s->q_d.p; args.ray_range = (const float2*)s->scratch_f[1].p; args.slot_hit = s->hit.p;
+    args.n_rays = (uint32_t)n; args.step_counters = s->seg_counter.p + 1;
+    k_bounce<SRC_RAYS, false><<<s->grid_bounce, 32 * PT_BOUNCE_WARPS, 0, st>>>(args);
+    k_unpack_hits<<<g, 256, 0, st>>>(n, scene_dev(s), s->q_o.p, s->q_d.p, s->hit.p, s->scratch_i[0].p,
                                      s->scratch_f[2].p, s->scratch_f[3].p, s->scratch_f[4].p);
     s->stats.launches += 3;
     CK(cudaGetLastError());

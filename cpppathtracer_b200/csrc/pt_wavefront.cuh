@@ -1,14 +1,16 @@
-// pt_wavefront.cuh -- the wavefront integrator stages (sm_100a).
+// pt_wavefront.cuh -- the wavefront integrator (sm_100a).
 //
-// The reference traces one full path per thread in a megakernel (SamplePixel,
-// cuSrc/path_tracer.cu:124-175), so a warp runs until its longest path ends and every material
-// branch is taken by every warp.  Here a wave of paths advances one segment per iteration through
-//     ray-gen -> [ closest-hit traversal -> bin by shader -> shade / miss -> compact survivors ] x depth -> accumulate
-// and the stages talk through SoA float4 queues in HBM:
-//     ray_o[slot] = (origin.xyz, bits pixel)      ray_d[slot] = (dir.xyz, bits sample-in-wave)
-//     thr[slot]   = (throughput.rgb, -)           hit[slot]   = (bits t, prim<<3 | part)   or code 0xFFFFFFFF = miss
-// Every stage is a persistent grid (a multiple of the SM count) whose warps pull work with one atomic
-// per warp and read the queue sizes from a device-side control block, so a whole frame is enqueued
+// The reference traces one full path per thread in a megakernel (SamplePixel, cuSrc/path_tracer.cu:124-175): a
+// warp runs until its longest path ends, every warp executes every material branch, and the RNG state round-trips
+// through global memory on every draw.  Here a wave of paths advances one segment per launch of k_bounce:
+//     launch 0      : camera rays                          -> closest hit -> hit queue 0, binned by shader
+//     launch k      : shade / miss the hits of segment k-1 -> survivors traced as segment k -> hit queue k
+//     launch depth  : shade / miss only
+//     k_accumulate  : wave radiance into the frame's SUM buffer, in sample order
+// Paths therefore leave the wave the moment they end (no idle lanes waiting for long paths), a warp shades with
+// ONE shader, and a ray lives in registers from the shader that creates it to the hit record it produces.
+// Every launch is a persistent grid (a multiple of the SM count) whose warps pull 32-item chunks with one atomic
+// per several chunks and read the queue sizes from a device-side control block, so a whole frame is enqueued
 // without a single host synchronisation.
 #pragma once
 #include "pt_math.cuh"
@@ -24,11 +26,11 @@ namespace pt {
 // waiting on ~300 k same-line atomics per launch (profiles/r01_v1_summary.md).
 struct Counter128 { uint32_t v; uint32_t pad[31]; };
 struct BounceCtrl {
-    Counter128 in_count;            // slots in the input queue of this bounce (holes included), written once
-    Counter128 rays;                // valid rays in that queue (statistics)
-    Counter128 trav_head;           // traversal work counter
-    Counter128 shade_head;          // shade work counter, in 32-item chunks
-    Counter128 bin_count[NUM_BINS]; // items per shader bin
+    Counter128 in_count;            // (parity path) rays in the caller's batch
+    Counter128 rays;                // rays traced as this segment (statistics)
+    Counter128 trav_head;           // unused since the fused bounce kernel (kept: layout)
+    Counter128 shade_head;          // work counter of the launch that CONSUMES this block's hit queue, in 32-item chunks
+    Counter128 bin_count[NUM_BINS]; // hits of this segment per shader bin
 };
 static_assert(sizeof(BounceCtrl) == 128 * (4 + NUM_BINS), "one line per counter");
 #define PT_INVALID_SLOT 0xFFFFFFFFu   // ray_o.w of a queue slot whose path ended (hole)
@@ -49,41 +51,6 @@ struct SceneDev {
     int has_emitters;
 };
 
-struct WaveQueues {
-    float4* ray_o[2];
-    float4* ray_d[2];
-    float4* thr[2];
-    uint2* hit;
-    // hit queues, one per shader bin (NUM_BINS x capacity each): the complete shading input of a finished ray
-    float4* hq_o; float4* hq_d; float4* hq_thr; uint2* hq_hit;
-    float4* path_out;         // per path of the wave: radiance (rgb, -)
-    BounceCtrl* ctrl;         // [max_depth + 1]
-    uint32_t capacity;
-};
-
-// ---- stage 0: camera rays (MotionalCamera::RayGen, motional_camera.cu:202-213) ----------------------
-__global__ void __launch_bounds__(256) k_raygen(CameraFrame cam, uint2 key, uint32_t npix, uint32_t n_paths,
-                                                uint32_t first_sample, float4* __restrict__ ray_o,
-                                                float4* __restrict__ ray_d, float4* __restrict__ thr,
-                                                float4* __restrict__ path_out, int zero_out,
-                                                BounceCtrl* __restrict__ ctrl0) {
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t pid = blockIdx.x * blockDim.x + threadIdx.x; pid < n_paths; pid += stride) {
-        const uint32_t s = pid / npix;
-        const uint32_t pixel = pid - s * npix;
-        const int y = pixel / (uint32_t)cam.width;
-        const int x = pixel - y * (uint32_t)cam.width;
-        float4 U = philox_uniform4(key, pixel, first_sample + s, 0u);
-        float3 o, d;
-        camera_ray(cam, x, y, U, o, d);
-        ray_o[pid] = make_float4(o.x, o.y, o.z, __uint_as_float(pixel));
-        ray_d[pid] = make_float4(d.x, d.y, d.z, __uint_as_float(s));
-        thr[pid] = make_float4(1.f, 1.f, 1.f, 0.f);
-        if (zero_out) path_out[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) { ctrl0->in_count.v = n_paths; ctrl0->rays.v = n_paths; }
-}
-
 // ---- stage 1: closest hit ------------------------------------------------------------------------------
 // Replaces SceneBVH::TraceRay + Object::IntersectionTest (bvh.cu:167-205, object.cu:10-128): near-child-first
 // stack traversal of the 64-byte LBVH nodes, tagged sphere / cylinder leaf test, platforms from the side list.
@@ -94,19 +61,9 @@ __global__ void __launch_bounds__(256) k_raygen(CameraFrame cam, uint2 key, uint
 // on the floor plane (video_renderer.cpp:78,105-106).  Device primitive indices ARE the reference's leaf
 // visiting order (upload_and_build in pt_api.cu), so a tied candidate wins iff its index is lower than the
 // current holder's: the intersector is then handed a tmax one ulp above best_t, so its `t < tmax` admits t == best_t.
-// Persistent warps with lane refill: a lane whose ray finished takes the next ray of the queue while its
-// neighbours keep walking, so a warp no longer idles until its longest ray ends (v1: 12.7 of 32 lanes active
-// per instruction).  Finished rays are staged per warp in shared memory and binned by shader 32 at a time,
-// one atomic per warp and bin.
-#ifndef PT_TRAV_WARPS
-#define PT_TRAV_WARPS 4
+#ifndef PT_BOUNCE_WARPS
+#define PT_BOUNCE_WARPS 4
 #endif
-#ifndef PT_TRAV_MIN_BLOCKS
-#define PT_TRAV_MIN_BLOCKS 1
-#endif
-#define PT_REFILL_MIN 32       // refill when at least this many lanes are idle (32: a warp refills as a whole;
-                               // measured on C2: partial refills gain nothing, profiles/r01_v2_sweep.md)
-#define PT_STEPS_PER_CHECK 8   // traversal rounds between two refill / retire checks
 
 struct LaneRay {
     float3 o, d;
@@ -199,245 +156,203 @@ __device__ __forceinline__ void lane_leaf(const SceneDev& sc, LaneRay& r, int* s
     }
 }
 
-// The hit queues: what a finished ray hands to the shade stage, one queue per shader bin, SoA float4:
-//   hq_o = (origin, bits pixel)  hq_d = (dir, bits sample)  hq_thr = (throughput)  hq_hit = (bits t, prim<<3|part)
-// The traversal warp that finished the rays also MOVES their records there (32 at a time, positions from one
-// atomic per warp and bin), so the shade stage streams its bin in order instead of gathering 16-byte pieces
-// through an index list (v3: 2x read amplification and a dependent DRAM round trip in k_shade).  The copy rides on
-// the memory system the ALU/L1-bound walk leaves idle (k_traverse used 2-7 % of DRAM bandwidth).
+// ---- the bounce kernel ---------------------------------------------------------------------------------------
+// One launch per path segment k.  A warp takes a 32-item chunk of its source, turns it into rays IN REGISTERS,
+// walks them to completion and files the results, binned by shader, into the hit queue of segment k:
+//   SRC_CAMERA : path ids        -> MotionalCamera::RayGen                      -> trace segment 0
+//   SRC_HITS   : hit queue k-1   -> shade / miss (one shader per chunk)         -> trace segment k (survivors)
+//   SRC_RAYS   : caller's rays   (parity entry point pt_trace_rays)             -> trace, results by ray slot
+// Rays never touch HBM: the only stage-to-stage traffic is the hit queue, one 56-byte record per segment,
+// SoA float4, written and read in order:
+//   hq.o = (origin, bits pixel)  hq.d = (dir, bits sample)  hq.thr = (throughput)  hq.hit = (bits t, prim<<3|part)
+// The launch after the last segment runs with trace = 0: it only shades what is left.
+// (v1-v4 kept rays in double-buffered HBM queues between a traverse and a shade kernel: 208 B per segment and
+// twice the launches; profiles/r01_v5_summary.md.)
 struct HitQueues {
     float4* o; float4* d; float4* thr; uint2* hit;
     uint32_t capacity;     // entries per bin
 };
-struct StageEntry { uint32_t slot_bin; uint32_t t; uint32_t code; };   // slot_bin = bin<<29 | slot
+enum { SRC_CAMERA = 0, SRC_HITS = 1, SRC_RAYS = 2 };
 
-__device__ __forceinline__ void flush_stage(StageEntry* stage, uint32_t& stage_n, uint32_t lane, BounceCtrl* ctrl,
-                                            const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
-                                            const float4* __restrict__ thr, const HitQueues& hq, bool everything) {
-    while (stage_n >= 32u || (everything && stage_n > 0u)) {
-        const uint32_t cnt = stage_n < 32u ? stage_n : 32u;
-        StageEntry e; e.slot_bin = 0xFFFFFFFFu; e.t = 0u; e.code = 0u;
-        if (lane < cnt) e = stage[lane];
-        const int bin = lane < cnt ? (int)(e.slot_bin >> 29) : -1;
-        const uint32_t slot = e.slot_bin & 0x1FFFFFFFu;
-        float4 o4 = make_float4(0, 0, 0, 0), d4 = o4, t4 = o4;
-        if (lane < cnt) { o4 = ray_o[slot]; d4 = ray_d[slot]; t4 = thr[slot]; }
-#pragma unroll
-        for (int b = 0; b < NUM_BINS; ++b) {
-            const uint32_t m = __ballot_sync(PT_FULL, bin == b);
-            if (m) {
-                uint32_t off = 0;
-                const int leader = __ffs(m) - 1;
-                if ((int)lane == leader) off = atomicAdd(&ctrl->bin_count[b].v, (uint32_t)__popc(m));
-                off = __shfl_sync(PT_FULL, off, leader);
-                if (bin == b) {
-                    const size_t j = (size_t)b * hq.capacity + off + __popc(m & ((1u << lane) - 1u));
-                    hq.o[j] = o4; hq.d[j] = d4; hq.thr[j] = t4; hq.hit[j] = make_uint2(e.t, e.code);
-                }
-            }
-        }
-        __syncwarp();
-        const uint32_t rest = stage_n - cnt;
-        StageEntry moved; moved.slot_bin = 0u; moved.t = 0u; moved.code = 0u;
-        if (lane < rest) moved = stage[32u + lane];
-        __syncwarp();
-        if (lane < rest) stage[lane] = moved;
-        stage_n = rest;
-        __syncwarp();
-    }
-}
+struct BounceArgs {
+    SceneDev sc;
+    uint2 key;
+    uint32_t npix, first_sample;
+    int segment;              // index k of the segment traced by this launch (shaded hits belong to k-1)
+    int max_depth;
+    int trace;                // 0: shade only (the launch after the last segment)
+    int inner_run;            // inner nodes a lane may walk before the warp regroups for primitive tests
+    CameraFrame cam;          // SRC_CAMERA
+    uint32_t n_paths;
+    HitQueues hq_in, hq_out;  // SRC_HITS reads hq_in (ctrl_in), every traced segment writes hq_out (ctrl_out)
+    BounceCtrl* ctrl_in;
+    BounceCtrl* ctrl_out;
+    float4* path_out;
+    float4* gbuf_normal;      // display pipeline only: first-segment normal per pixel
+    const float4* ray_o;      // SRC_RAYS
+    const float4* ray_d;
+    const float2* ray_range;
+    uint2* slot_hit;
+    uint32_t n_rays;
+    unsigned long long* step_counters;   // COUNT_STEPS: [0] inner nodes visited, [1] primitive tests
+};
 
-template <bool PER_RAY_RANGE, bool COUNT_STEPS>
-__global__ void __launch_bounds__(32 * PT_TRAV_WARPS, PT_TRAV_MIN_BLOCKS) k_traverse(SceneDev sc, const float4* __restrict__ ray_o,
-                                                                const float4* __restrict__ ray_d,
-                                                                const float4* __restrict__ ray_thr,
-                                                                const float2* __restrict__ ray_range, float tmin_all,
-                                                                BounceCtrl* __restrict__ ctrl, uint2* __restrict__ slot_hit,
-                                                                HitQueues hq, uint32_t refill_min, int steps_per_check,
-                                                                int inner_run,
-                                                                unsigned long long* __restrict__ step_counters) {
-    __shared__ StageEntry s_stage[PT_TRAV_WARPS][64];
+template <int SRC, bool COUNT_STEPS>
+__global__ void __launch_bounds__(32 * PT_BOUNCE_WARPS) k_bounce(const BounceArgs a) {
     const uint32_t lane = threadIdx.x & 31u;
-    StageEntry* stage = s_stage[threadIdx.x >> 5];
-    uint32_t stage_n = 0;
-    const uint32_t n = ctrl->in_count.v;
-    int stack[PT_STACK];
-    LaneRay r;
-    r.node = PT_SENTINEL; r.sp = 0; r.slot = 0; r.best_t = 0.f; r.best_code = PT_MISS_CODE; r.tmin = 0.f;
-    r.o = r.d = f3(0.f, 0.f, 0.f); r.ix = r.iy = r.iz = r.ox = r.oy = r.oz = r.slack = 0.f;
-    bool active = false;
-    bool exhausted = false;     // warp-uniform: the queue has no more rays to hand out
-    uint32_t n_inner = 0, n_leaf = 0;   // COUNT_STEPS only
-    while (true) {
-        // ---- refill idle lanes ----
-        const uint32_t idle = __ballot_sync(PT_FULL, !active);
-        if (idle != 0u && !exhausted && ((uint32_t)__popc(idle) >= refill_min || idle == PT_FULL)) {
-            const uint32_t want = (uint32_t)__popc(idle);
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(&ctrl->trav_head.v, want);
-            base = __shfl_sync(PT_FULL, base, 0);
-            if (base + want >= n) exhausted = true;
-            if (!active) {
-                const uint32_t slot = base + __popc(idle & ((1u << lane) - 1u));
-                if (slot < n) {
-                    const float4 o4 = ray_o[slot];
-                    if (__float_as_uint(o4.w) != PT_INVALID_SLOT) {
-                        const float4 d4 = ray_d[slot];
-                        r.o = f3(o4.x, o4.y, o4.z); r.d = f3(d4.x, d4.y, d4.z);
-                        r.tmin = tmin_all; r.best_t = PT_TMAX;
-                        if (PER_RAY_RANGE) { const float2 rr = ray_range[slot]; r.tmin = rr.x; r.best_t = rr.y; }
-                        r.slot = slot;
-                        lane_begin(sc, r, stack);
-                        active = true;
-                    }
-                }
-            }
-        }
-        if (!__any_sync(PT_FULL, active)) {
-            if (exhausted) break;
-            continue;                       // a refill that only found holes: fetch again
-        }
-        // ---- walk ----
-        // while-while: a lane first runs down inner nodes (up to inner_run of them), then tests the leaf it
-        // reached; the warp reconverges between the two so node steps and primitive tests each run with as many
-        // lanes as possible instead of interleaving (v1 "if-if": 12.7 of 32 lanes active per instruction)
-#pragma unroll 1
-        for (int it = 0; it < steps_per_check; ++it) {
-            if (active) {
-                int k = 0;
-#pragma unroll 1
-                while (r.node >= 0 && r.node != PT_SENTINEL && k < inner_run) { lane_inner(sc, r, stack); ++k; if (COUNT_STEPS) ++n_inner; }
-            }
-            if (active && r.node < 0) { lane_leaf(sc, r, stack); if (COUNT_STEPS) ++n_leaf; }
-        }
-        // ---- retire finished lanes ----
-        const bool fin = active && r.node == PT_SENTINEL;
-        const uint32_t fm = __ballot_sync(PT_FULL, fin);
-        if (fm) {
-            if (fin) {
-                // the parity entry point (pt_trace_rays) reads results by ray slot; the render path does not
-                if (PER_RAY_RANGE) slot_hit[r.slot] = make_uint2(__float_as_uint(r.best_t), r.best_code);
-                const uint32_t bin = (r.best_code == PT_MISS_CODE)
-                                         ? (uint32_t)BIN_MISS
-                                         : (__float_as_uint(__ldg(&sc.geo1[r.best_code >> 3]).w) >> 28);
-                StageEntry e; e.slot_bin = (bin << 29) | r.slot; e.t = __float_as_uint(r.best_t); e.code = r.best_code;
-                stage[stage_n + __popc(fm & ((1u << lane) - 1u))] = e;
-                active = false;
-            }
-            stage_n += (uint32_t)__popc(fm);
-            __syncwarp();
-            flush_stage(stage, stage_n, lane, ctrl, ray_o, ray_d, ray_thr, hq, false);
-        }
-    }
-    flush_stage(stage, stage_n, lane, ctrl, ray_o, ray_d, ray_thr, hq, true);
-    if (COUNT_STEPS) {
+    const SceneDev& sc = a.sc;
+    // ---- work list: 32-item chunks; SRC_HITS chunks never straddle two shader bins ----
+    uint32_t chunk_end[NUM_BINS], bin_n[NUM_BINS];
+    uint32_t total = 0;
+    if (SRC == SRC_HITS) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { n_inner += __shfl_xor_sync(PT_FULL, n_inner, o); n_leaf += __shfl_xor_sync(PT_FULL, n_leaf, o); }
-        if (lane == 0) { atomicAdd(&step_counters[0], (unsigned long long)n_inner); atomicAdd(&step_counters[1], (unsigned long long)n_leaf); }
-    }
-}
-
-// ---- stage 2: shade / miss, binned by shader; survivors are compacted into the next ray queue ------------
-// Replaces Object::ClosetHit -> Material::EvalAttenuationAndCreateRay (object.cu:130-132, material.cu:145-163),
-// Miss (path_tracer.cu:117-122) and the per-segment bookkeeping of SamplePixel (path_tracer.cu:156-170).
-__global__ void __launch_bounds__(128) k_shade(SceneDev sc, uint2 key, uint32_t npix, uint32_t first_sample,
-                                               int bounce, int max_depth, HitQueues hq, BounceCtrl* __restrict__ ctrl,
-                                               BounceCtrl* __restrict__ ctrl_next, float4* __restrict__ out_o,
-                                               float4* __restrict__ out_d, float4* __restrict__ out_thr,
-                                               float4* __restrict__ path_out, float4* __restrict__ gbuf_normal) {
-    const uint32_t lane = threadIdx.x & 31u;
-    // Work items are 32-item chunks of the five shader bins, so a warp never mixes shaders.  The output slot of
-    // a hit item is a pure function of (bin, item): next queue = [diffuse | glossy | mix | glass] survivors in bin
-    // order.  No atomics for the compaction (v1 took one same-address atomic per warp here); the few paths that
-    // die with zero throughput leave a hole marked PT_INVALID_SLOT that the next traversal skips.
-    uint32_t chunk_end[NUM_BINS], bin_n[NUM_BINS], out_base[NUM_BINS];
-    uint32_t total = 0, next_n = 0;
+        for (int b = 0; b < NUM_BINS; ++b) { bin_n[b] = a.ctrl_in->bin_count[b].v; total += (bin_n[b] + 31u) >> 5; chunk_end[b] = total; }
+    } else {
+        const uint32_t n = SRC == SRC_CAMERA ? a.n_paths : a.n_rays;
+        total = (n + 31u) >> 5;
 #pragma unroll
-    for (int b = 0; b < NUM_BINS; ++b) {
-        bin_n[b] = ctrl->bin_count[b].v;
-        total += (bin_n[b] + 31u) >> 5; chunk_end[b] = total;
-        out_base[b] = next_n;
-        if (b != BIN_MISS) next_n += bin_n[b];
+        for (int b = 0; b < NUM_BINS; ++b) { bin_n[b] = n; chunk_end[b] = total; }
     }
-    const bool last_bounce = bounce + 1 >= max_depth;
-    if (!last_bounce && blockIdx.x == 0 && threadIdx.x == 0) ctrl_next->in_count.v = next_n;
-    // chunks taken per atomic: enough work per grab to keep the head counter cold, small enough to balance the tail
     const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
-    uint32_t grab = total / (n_warps * 4u);
-    grab = grab < 1u ? 1u : (grab > 8u ? 8u : grab);
-    uint32_t alive_count = 0;
+    uint32_t grab = total / (n_warps * 8u);          // chunks per atomic: keeps the head counter cold, balances the tail
+    grab = grab < 1u ? 1u : (grab > 4u ? 4u : grab);
+    const bool last_shade = a.segment >= a.max_depth;   // the hits being shaded belong to the last allowed segment
+    const float tmin = a.segment == 0 ? 0.f : PT_BOUNCE_TMIN;
+    uint32_t traced = 0, n_inner = 0, n_leaf = 0;
+    int stack[PT_STACK];
     while (true) {
         uint32_t first = 0;
-        if (lane == 0) first = atomicAdd(&ctrl->shade_head.v, grab);
+        if (lane == 0) first = atomicAdd(&a.ctrl_in->shade_head.v, grab);
         first = __shfl_sync(PT_FULL, first, 0);
         if (first >= total) break;
         const uint32_t end = first + grab < total ? first + grab : total;
         for (uint32_t chunk = first; chunk < end; ++chunk) {
-            int bin = 0;
-            uint32_t first_chunk = 0u, n_bin = bin_n[0], base_bin = out_base[0];
+            // ================= 1. a ray per lane, in registers =================
+            bool alive = false;
+            float3 thr = f3(1.f, 1.f, 1.f);
+            uint32_t pixel = 0, s = 0, slot = 0;
+            LaneRay r;
+            r.tmin = tmin; r.best_t = PT_TMAX; r.best_code = PT_MISS_CODE; r.node = PT_SENTINEL; r.sp = 0;
+            r.o = r.d = f3(0.f, 0.f, 0.f); r.ix = r.iy = r.iz = r.ox = r.oy = r.oz = r.slack = 0.f;
+            if (SRC == SRC_CAMERA) {
+                const uint32_t pid = (chunk << 5) + lane;
+                if (pid < a.n_paths) {
+                    s = pid / a.npix;
+                    pixel = pid - s * a.npix;
+                    const int y = pixel / (uint32_t)a.cam.width;
+                    const int x = pixel - y * (uint32_t)a.cam.width;
+                    const float4 U = philox_uniform4(a.key, pixel, a.first_sample + s, 0u);
+                    camera_ray(a.cam, x, y, U, r.o, r.d);
+                    if (sc.has_emitters) a.path_out[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    alive = true;
+                }
+            } else if (SRC == SRC_RAYS) {
+                slot = (chunk << 5) + lane;
+                if (slot < a.n_rays) {
+                    const float4 o4 = a.ray_o[slot], d4 = a.ray_d[slot];
+                    const float2 rr = a.ray_range[slot];
+                    r.o = f3(o4.x, o4.y, o4.z); r.d = f3(d4.x, d4.y, d4.z); r.tmin = rr.x; r.best_t = rr.y;
+                    alive = true;
+                }
+            } else {
+                // which bin does this chunk belong to
+                int bin = 0;
+                uint32_t first_chunk = 0u, n_bin = bin_n[0];
 #pragma unroll
-            for (int b = 1; b < NUM_BINS; ++b)
-                if (chunk >= chunk_end[b - 1]) { bin = b; first_chunk = chunk_end[b - 1]; n_bin = bin_n[b]; base_bin = out_base[b]; }
-            const uint32_t item = ((chunk - first_chunk) << 5) + lane;
-            const bool valid = item < n_bin;
-            if (!valid) continue;
-            const size_t q = (size_t)bin * hq.capacity + item;
-            const float4 o4 = hq.o[q];
-            const float4 d4 = hq.d[q];
-            const float4 t4 = hq.thr[q];
-            const uint2 h = hq.hit[q];
-            const uint32_t pixel = __float_as_uint(o4.w);
-            const uint32_t s = __float_as_uint(d4.w);
-            const size_t pid = (size_t)s * npix + pixel;
-            const float3 o = f3(o4.x, o4.y, o4.z), d = f3(d4.x, d4.y, d4.z);
-            float3 thr = f3(t4.x, t4.y, t4.z);
-            if (bin == BIN_MISS) {
-                const float3 c = thr * sky_radiance(sc.sky, d);
-                if (sc.has_emitters) { float4 p = path_out[pid]; path_out[pid] = make_float4(p.x + c.x, p.y + c.y, p.z + c.z, 0.f); }
-                else path_out[pid] = make_float4(c.x, c.y, c.z, 0.f);
-                // G-buffer of the display pipeline: a first-segment miss records -dir (path_tracer.cu:152)
-                if (gbuf_normal != nullptr && bounce == 0) gbuf_normal[pid] = make_float4(-d.x, -d.y, -d.z, 0.f);
+                for (int b = 1; b < NUM_BINS; ++b)
+                    if (chunk >= chunk_end[b - 1]) { bin = b; first_chunk = chunk_end[b - 1]; n_bin = bin_n[b]; }
+                const uint32_t item = ((chunk - first_chunk) << 5) + lane;
+                if (item < n_bin) {
+                    const size_t q = (size_t)bin * a.hq_in.capacity + item;
+                    const float4 o4 = a.hq_in.o[q];
+                    const float4 d4 = a.hq_in.d[q];
+                    const float4 t4 = a.hq_in.thr[q];
+                    const uint2 h = a.hq_in.hit[q];
+                    pixel = __float_as_uint(o4.w);
+                    s = __float_as_uint(d4.w);
+                    const size_t pid = (size_t)s * a.npix + pixel;
+                    const float3 o = f3(o4.x, o4.y, o4.z), d = f3(d4.x, d4.y, d4.z);
+                    thr = f3(t4.x, t4.y, t4.z);
+                    if (bin == BIN_MISS) {
+                        // Miss, path_tracer.cu:117-122: the path ends with the sky seen through its throughput
+                        const float3 c = thr * sky_radiance(sc.sky, d);
+                        if (sc.has_emitters) { float4 p = a.path_out[pid]; a.path_out[pid] = make_float4(p.x + c.x, p.y + c.y, p.z + c.z, 0.f); }
+                        else a.path_out[pid] = make_float4(c.x, c.y, c.z, 0.f);
+                        // G-buffer of the display pipeline: a first-segment miss records -dir (path_tracer.cu:152)
+                        if (a.gbuf_normal != nullptr && a.segment == 1) a.gbuf_normal[pid] = make_float4(-d.x, -d.y, -d.z, 0.f);
+                    } else {
+                        const uint32_t prim = h.y >> 3;
+                        const float4 g0 = __ldg(&sc.geo0[prim]);
+                        const uint32_t mslot = __float_as_uint(__ldg(&sc.geo1[prim]).w) & 0x0fffffffu;
+                        const MaterialRec m = sc.mats[mslot];
+                        float3 pos, normal;
+                        hit_attributes(g0, (int)(h.y & 7u), o, d, __uint_as_float(h.x), pos, normal);
+                        if (a.gbuf_normal != nullptr && a.segment == 1) a.gbuf_normal[pid] = make_float4(normal.x, normal.y, normal.z, 0.f);
+                        const float4 U = philox_uniform4(a.key, pixel, a.first_sample + s, (uint32_t)a.segment);   // slot 1 + (k-1)
+                        Scatter sct;
+                        shade_bin(bin, m, normal, d, U, sct);
+                        if (sc.has_emitters) {
+                            const float3 c = thr * sct.radiance;
+                            float4 p = a.path_out[pid];
+                            a.path_out[pid] = make_float4(p.x + c.x, p.y + c.y, p.z + c.z, 0.f);
+                        }
+                        thr = thr * sct.atten;
+                        // a path whose throughput is exactly zero can add nothing more (finite sky and emission): ending it
+                        // here is result-identical to the reference, which keeps bouncing it (path_tracer.cu:141-170)
+                        alive = !last_shade && (thr.x != 0.f || thr.y != 0.f || thr.z != 0.f);
+                        if (!alive && !sc.has_emitters) a.path_out[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (alive) { r.o = pos; r.d = normalize(sct.bounce); }
+                    }
+                }
+            }
+            if (!a.trace) continue;
+            // ================= 2. walk: while-while, the warp regroups between node runs and primitive tests =================
+            if (alive) { lane_begin(sc, r, stack); ++traced; }
+            while (__any_sync(PT_FULL, alive && r.node != PT_SENTINEL)) {
+                if (alive) {
+                    int k = 0;
+#pragma unroll 1
+                    while (r.node >= 0 && r.node != PT_SENTINEL && k < a.inner_run) { lane_inner(sc, r, stack); ++k; if (COUNT_STEPS) ++n_inner; }
+                }
+                if (alive && r.node < 0) { lane_leaf(sc, r, stack); if (COUNT_STEPS) ++n_leaf; }
+            }
+            // ================= 3. file the results =================
+            if (SRC == SRC_RAYS) {
+                if (alive) a.slot_hit[slot] = make_uint2(__float_as_uint(r.best_t), r.best_code);
                 continue;
             }
-            const uint32_t prim = h.y >> 3;
-            const float4 g0 = __ldg(&sc.geo0[prim]);
-            const uint32_t mslot = __float_as_uint(__ldg(&sc.geo1[prim]).w) & 0x0fffffffu;
-            const MaterialRec m = sc.mats[mslot];
-            float3 pos, normal;
-            hit_attributes(g0, (int)(h.y & 7u), o, d, __uint_as_float(h.x), pos, normal);
-            if (gbuf_normal != nullptr && bounce == 0) gbuf_normal[pid] = make_float4(normal.x, normal.y, normal.z, 0.f);
-            const float4 U = philox_uniform4(key, pixel, first_sample + s, 1u + (uint32_t)bounce);
-            Scatter sct;
-            shade_bin(bin, m, normal, d, U, sct);
-            if (sc.has_emitters) {
-                const float3 c = thr * sct.radiance;
-                float4 p = path_out[pid];
-                path_out[pid] = make_float4(p.x + c.x, p.y + c.y, p.z + c.z, 0.f);
-            }
-            thr = thr * sct.atten;
-            // a path whose throughput is exactly zero can add nothing more (finite sky and emission):
-            // ending it here is result-identical to the reference, which keeps bouncing it (path_tracer.cu:141-170)
-            const bool alive = !last_bounce && (thr.x != 0.f || thr.y != 0.f || thr.z != 0.f);
-            if (!alive && !sc.has_emitters) path_out[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (!last_bounce) {
-                const uint32_t j = base_bin + item;
-                if (alive) {
-                    const float3 ndir = normalize(sct.bounce);
-                    out_o[j] = make_float4(pos.x, pos.y, pos.z, __uint_as_float(pixel));
-                    out_d[j] = make_float4(ndir.x, ndir.y, ndir.z, __uint_as_float(s));
-                    out_thr[j] = make_float4(thr.x, thr.y, thr.z, 0.f);
-                    ++alive_count;
-                } else {
-                    out_o[j] = make_float4(0.f, 0.f, 0.f, __uint_as_float(PT_INVALID_SLOT));
+            int obin = -1;
+            if (alive)
+                obin = (r.best_code == PT_MISS_CODE) ? BIN_MISS : (int)(__float_as_uint(__ldg(&sc.geo1[r.best_code >> 3]).w) >> 28);
+#pragma unroll
+            for (int b = 0; b < NUM_BINS; ++b) {
+                const uint32_t m = __ballot_sync(PT_FULL, obin == b);
+                if (m) {
+                    uint32_t off = 0;
+                    const int leader = __ffs(m) - 1;
+                    if ((int)lane == leader) off = atomicAdd(&a.ctrl_out->bin_count[b].v, (uint32_t)__popc(m));
+                    off = __shfl_sync(PT_FULL, off, leader);
+                    if (obin == b) {
+                        const size_t j = (size_t)b * a.hq_out.capacity + off + __popc(m & ((1u << lane) - 1u));
+                        a.hq_out.o[j] = make_float4(r.o.x, r.o.y, r.o.z, __uint_as_float(pixel));
+                        a.hq_out.d[j] = make_float4(r.d.x, r.d.y, r.d.z, __uint_as_float(s));
+                        a.hq_out.thr[j] = make_float4(thr.x, thr.y, thr.z, 0.f);
+                        a.hq_out.hit[j] = make_uint2(__float_as_uint(r.best_t), r.best_code);
+                    }
                 }
             }
         }
     }
-    // statistics: valid rays handed to the next bounce (one atomic per warp per launch)
-    if (!last_bounce) {
+    // statistics: rays traced by this launch (one atomic per warp), optional visit counters
+    if (a.trace) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) alive_count += __shfl_xor_sync(PT_FULL, alive_count, o);
-        if (lane == 0 && alive_count) atomicAdd(&ctrl_next->rays.v, alive_count);
+        for (int o = 16; o > 0; o >>= 1) traced += __shfl_xor_sync(PT_FULL, traced, o);
+        if (lane == 0 && traced) atomicAdd(&a.ctrl_out->rays.v, traced);
+    }
+    if (COUNT_STEPS) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { n_inner += __shfl_xor_sync(PT_FULL, n_inner, o); n_leaf += __shfl_xor_sync(PT_FULL, n_leaf, o); }
+        if (lane == 0) { atomicAdd(&a.step_counters[0], (unsigned long long)n_inner); atomicAdd(&a.step_counters[1], (unsigned long long)n_leaf); }
     }
 }
 
@@ -462,7 +377,7 @@ __global__ void __launch_bounds__(256) k_accumulate(uint32_t npix, uint32_t n_sa
 __global__ void k_wave_stats(int max_depth, const BounceCtrl* __restrict__ ctrl, unsigned long long* __restrict__ segments) {
     // segments[0] rays traced, [1] inner-node steps, [2] primitive tests (the latter two only with PT_OPT_COUNT_STEPS)
     unsigned long long n = 0;
-    for (int b = 0; b < max_depth; ++b) n += ctrl[b].rays.v;
+    for (int b = 0; b < max_depth; ++b) n += ctrl[b].rays.v;   // ctrl[k].rays = rays traced as segment k
     *segments += n;
 }
 

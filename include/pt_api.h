@@ -64,12 +64,12 @@ typedef struct pt_stats {
     uint64_t segments;        /* rays (path segments) traced                                  */
     uint64_t launches;        /* kernels launched by this scene since creation                */
     float    render_ms;       /* device time of the last pt_render_frame (CUDA events)        */
-    float    traverse_ms;     /* ... of which closest-hit traversal (only with PT_OPT_STAGE_TIMING) */
-    float    shade_ms;        /* ... shade + miss                                             */
+    float    traverse_ms;     /* ... of which the launches that trace a segment (only with PT_OPT_STAGE_TIMING) */
+    float    shade_ms;        /* ... the final shade-only launch                              */
     float    build_ms;        /* device time of the last pt_build                             */
     uint32_t bvh_nodes;
     uint32_t wave_paths;      /* paths in flight per wave                                     */
-    uint32_t traverse_launches; /* closest-hit launches of the last pt_render_frame (= waves x depth) */
+    uint32_t traverse_launches; /* tracing launches of the last pt_render_frame (= waves x depth)    */
     uint32_t waves;           /* waves of the last pt_render_frame                            */
     uint64_t node_steps;      /* inner BVH nodes visited (only with PT_OPT_COUNT_STEPS)       */
     uint64_t prim_tests;      /* sphere / cylinder tests run (only with PT_OPT_COUNT_STEPS)   */
@@ -82,8 +82,6 @@ enum {
                                  visiting order (bvh.cu:31-90,167-205); 0: lowest primitive id wins */
     PT_OPT_SKY_QUARTER_ROWS = 4, /* 1 (default): reproduce the reference's upload that copies `width`
                                  BYTES per row (cuSrc/textures.cu:32); 0: upload whole rows         */
-    PT_OPT_TRAV_REFILL_MIN = 5, /* tuning: idle lanes per warp that trigger a ray refill (1..32)     */
-    PT_OPT_TRAV_STEPS = 6,      /* tuning: traversal rounds between two refill / retire checks       */
     PT_OPT_COUNT_STEPS = 8,     /* 1: use the instrumented traversal kernel that counts node visits / primitive tests */
     PT_OPT_TRAV_INNER_RUN = 7   /* tuning: inner-node steps a lane may take before the warp regroups for leaf tests */
 };

@@ -9,5 +9,5 @@ for which in sys.argv[1:] or ["c2"]:
     for _ in range(3):
         r.reset_accum(); r.render(sc.camera, spp, 8, seed=2026)
     st = r.stats()
-    print(f"{which}: {st['paths']/st['render_ms']/1e3:7.1f} Mpaths/s  trav {st['traverse_ms']:.2f} shade {st['shade_ms']:.2f} total {st['render_ms']:.2f} build {st['build_ms']:.2f}", flush=True)
+    print(f"{which}: {st['paths']/st['render_ms']/1e3:7.1f} Mpaths/s  trace-launches {st["traverse_ms"]:.2f} tail {st["shade_ms"]:.2f} total {st['render_ms']:.2f} build {st['build_ms']:.2f}", flush=True)
     r.close()
