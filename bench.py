@@ -29,10 +29,14 @@ import numpy as np  # noqa: E402
 METRIC = "Mpaths/s at 1080p, max depth 8"
 WORKLOAD = {"workload": "C2: floor + 1000 mixed-material spheres, 1920x1080, 64 spp, depth 8",
             "width": 1920, "height": 1080, "spp": 64, "max_depth": 8, "n_spheres": 1000, "scene_seed": 12345,
-            "l2": "wave queues (>1.5 GB per 8-spp wave) exceed the 126 MB L2; no explicit flush"}
-ALG_BYTES_PER_RAY_TRAVERSE = 40      # read ray origin+dir (2 x float4 = 32 B) + write hit record (8 B), DESIGN.md
-ALG_BYTES_PER_SEGMENT = 144          # whole-path queue traffic per segment
-ALG_BYTES_PER_PATH = 16              # + one float4 radiance write per path
+            "l2": "hit queues (3.7 GB streamed per 16-spp wave) exceed the 126 MB L2; no explicit flush"}
+# Algorithmic HBM bytes of the dominant kernel k_bounce: every path segment costs one
+# 56-byte hit record written by the launch that traces it and read by the launch that shades it (rays never leave
+# registers), every path one 16-byte radiance write.  SURVEY.md 8(d) budgets 144 B/segment + 16 B/path for a
+# wavefront design that also keeps rays in HBM; that figure is reported beside this one.
+ALG_BYTES_PER_SEGMENT = 112
+ALG_BYTES_PER_PATH = 16
+SURVEY_BYTES_PER_SEGMENT = 144
 
 
 def measured_peaks():
@@ -292,33 +296,35 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peaks()
         segs = st["segments"]                      # rays traced in the last frame on this rank
-        trav_ms = st["traverse_ms"]
-        n_trav = max(st["traverse_launches"], 1)
-        achieved = ALG_BYTES_PER_RAY_TRAVERSE * segs / (trav_ms * 1e-3) / 1e9 if trav_ms > 0 else None
+        kern_ms = st["traverse_ms"] + st["shade_ms"]   # all k_bounce launches of the last frame (CUDA events per launch)
+        n_launch = max(st["waves"] * (depth + 1), 1)
+        alg_bytes = ALG_BYTES_PER_SEGMENT * segs + ALG_BYTES_PER_PATH * st["paths"]
+        achieved = alg_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else None
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traverse_traffic.json")
         if os.path.exists(tp):
             with open(tp) as f:
                 traffic = json.load(f).get("dram_bytes_per_launch")
-        path_bytes = ALG_BYTES_PER_SEGMENT * segs + ALG_BYTES_PER_PATH * st["paths"]
         line = {
             "metric": METRIC, "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": dict(WORKLOAD, parallelism=f"spp-sharded x{world}, one NCCL reduce per frame" if world > 1 else "single GPU",
                            spp_total=spp * world, wave_paths=st["wave_paths"]),
-            "roofline": {"bound": "hbm", "kernel": "k_traverse (closest hit)", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                         "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": ALG_BYTES_PER_RAY_TRAVERSE * segs / n_trav,
-                         "avg_launch_ms": trav_ms / n_trav, "launches_per_step": n_trav,
-                         "share_of_step": trav_ms / st["render_ms"] if st["render_ms"] > 0 else None,
-                         "note": "latency/issue-bound BVH walk: the HBM roofline is reported as the contract asks, "
-                                 "see DESIGN.md for the FP32-issue view"},
+            "roofline": {"bound": "hbm", "kernel": "k_bounce (shade previous hits + trace the segment, fused)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                         "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes / n_launch, "avg_launch_ms": kern_ms / n_launch,
+                         "launches_per_step": n_launch,
+                         "share_of_step": kern_ms / st["render_ms"] if st["render_ms"] > 0 else None,
+                         "note": "the kernel is bound by instruction issue / the ALU pipe (IPC 2.5-3.1 of 4, ALU pipe 51-67 %, "
+                                 "17-27 of 32 lanes active, profiles/r01_v5_summary.md), not by HBM; DRAM traffic equals the "
+                                 "algorithmic bytes (ratio 1.006)"},
             "path": {"mrays_per_s": segs / (st["render_ms"] * 1e-3) / 1e6 if st["render_ms"] > 0 else None,
                      "segments_per_path": segs / st["paths"], "render_ms_last_frame": st["render_ms"],
-                     "traverse_ms": trav_ms, "shade_ms": st["shade_ms"],
-                     "queue_hbm_gbs_model": path_bytes / (st["render_ms"] * 1e-3) / 1e9 if st["render_ms"] > 0 else None},
+                     "bounce_kernel_ms": kern_ms,
+                     "hbm_gbs_at_survey_model": (SURVEY_BYTES_PER_SEGMENT * segs + ALG_BYTES_PER_PATH * st["paths"]) / (st["render_ms"] * 1e-3) / 1e9
+                     if st["render_ms"] > 0 else None},
             "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "what": "pt_update_prim + pt_build (upload, LBVH) + pt_render_frame + pt_read_accum into pinned host memory"},
             "gpu_launches": int(launches), "clocks": clocks,

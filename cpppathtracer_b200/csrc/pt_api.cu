@@ -71,7 +71,7 @@ struct pt_scene {
     std::map<MatKey, int> material_slots;
     bool dirty = true, built = false;
     // options
-    uint32_t opt_wave_paths = 16u << 20;
+    uint32_t opt_wave_paths = 32u << 20;   // 16 spp per wave at 1080p: 19 GB of hit queues, +3 % over 16 Mi (profiles/r01_v5_summary.md)
     int opt_stage_timing = 0;
     int opt_tie_order = 1;
     int opt_sky_quarter = 1;

@@ -1,4 +1,4 @@
-"""Profiling target: C2 scene, 1920x1080, 8 spp (= one 16.6 M-path wave) per frame, depth 8.  Same kernels
+"""Profiling target: C2 scene, 1920x1080, 16 spp (= one 33.2 M-path wave) per frame, depth 8.  Same kernels
 and launch shapes as bench.py's step (which is 8 such waves)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -8,7 +8,7 @@ sc = scenes.sphere_field(1000, 1920, 1080)
 r = api.Renderer(sc, scenes.synthetic_sky(1280, 1280))
 for f in range(frames):
     r.reset_accum()
-    r.render(sc.camera, 8, 8, seed=2026)
+    r.render(sc.camera, 16, 8, seed=2026)
 st = r.stats()
 print(f"{st['paths'] / st['render_ms'] / 1e3:.1f} Mpaths/s, render_ms {st['render_ms']:.2f}, segments {st['segments']}")
 r.close()
