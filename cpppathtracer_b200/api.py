@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpt_b200.so")
 
 PT_OPT_WAVE_PATHS, PT_OPT_STAGE_TIMING, PT_OPT_TIE_ORDER, PT_OPT_SKY_QUARTER_ROWS = 1, 2, 3, 4
-PT_OPT_TRAV_INNER_RUN, PT_OPT_COUNT_STEPS = 7, 8
+PT_OPT_TRAV_INNER_RUN, PT_OPT_COUNT_STEPS, PT_OPT_REF_LEAF_BOXES = 7, 8, 9
 
 
 class PtMaterial(C.Structure):
@@ -41,7 +41,7 @@ EXPORTS = [
     "pt_scene_create", "pt_scene_destroy", "pt_set_option", "pt_set_stream", "pt_add_sphere", "pt_add_platform",
     "pt_add_cylinder", "pt_set_material", "pt_update_prim", "pt_set_sky_rgba8", "pt_build", "pt_render_frame",
     "pt_render_frame_async", "pt_synchronize", "pt_reset_accum", "pt_read_accum", "pt_accum_device_ptr",
-    "pt_get_stats", "pt_dispatch_ray", "pt_texture_create_rgba8", "pt_texture_destroy", "pt_trace_rays",
+    "pt_get_stats", "pt_dispatch_ray", "pt_texture_create_rgba8", "pt_texture_destroy", "pt_trace_rays", "pt_last_trace_steps",
     "pt_shade_batch", "pt_raygen_batch", "pt_sky_lookup", "pt_philox_uniforms", "pt_camera_basis", "pt_camera_control",
     "pt_last_error",
     "pt_version",
@@ -271,6 +271,11 @@ class Renderer:
         self._check(self.lib.pt_trace_rays(self.h, n, rays8.ctypes.data, prim.ctypes.data, t.ctypes.data,
                                            nrm.ctypes.data, pos.ctypes.data))
         return prim, t, nrm, pos
+
+    def last_trace_steps(self, n: int) -> np.ndarray:
+        out = np.empty(n, np.uint32)
+        self._check(self.lib.pt_last_trace_steps(self.h, C.c_int(n), C.c_void_p(out.ctypes.data)))
+        return out
 
     def shade(self, materials: np.ndarray, mat_idx, pos, nrm, in_dir, u3):
         n = len(mat_idx)

@@ -76,9 +76,10 @@ struct pt_scene {
     int opt_tie_order = 1;
     int opt_sky_quarter = 1;
     int opt_count_steps = 0;
+    int opt_ref_leaf_boxes = 0;
     int opt_inner_run = 4;
     // device scene
-    DevBuf<float4> geo0, geo1, nodes, leaf_mn, leaf_mx, inner_mn, inner_mx;
+    DevBuf<float4> geo0, geo1, nodes, leaf_mn, leaf_mx, leaf_c, inner_mn, inner_mx, test_mn, test_mx;
     DevBuf<MaterialRec> mats;
     DevBuf<float> plat_y;
     DevBuf<int> plat_id, bvh_prims, parent_inner, parent_leaf, flags;
@@ -205,10 +206,12 @@ int material_slot(pt_scene* s, const pt_material& m_in) {
 struct RefOrder {
     const std::vector<HostPrim>& prims;
     std::vector<float> mn, mx;   // 3 floats per prim, Object::GetAABBMin/Max (object.cu:134-170)
+    std::vector<float> pmn, pmx; // 3 floats per prim: box of the reference node whose split made the prim a leaf
     std::vector<int> order;
     explicit RefOrder(const std::vector<HostPrim>& p) : prims(p) {
         const float tol = PT_BOUNCE_TMIN * 5.f;
         mn.resize(3 * p.size()); mx.resize(3 * p.size()); order.resize(p.size());
+        pmn.assign(3 * p.size(), 0.f); pmx.assign(3 * p.size(), 0.f);
         for (size_t i = 0; i < p.size(); ++i) {
             const HostPrim& o = p[i];
             float ar = o.radius >= 0 ? o.radius : -o.radius;
@@ -241,6 +244,10 @@ struct RefOrder {
             return (MN[3 * a + axis] + MX[3 * a + axis]) / 2 < (MN[3 * b + axis] + MX[3 * b + axis]) / 2;
         });
         int mid = (l + r) / 2;
+        // TraceRay tests a leaf's object whenever the leaf is popped, i.e. whenever its PARENT's box was hit
+        // (bvh.cu:175-180,200-202): remember that box for the leaves this split creates
+        if (mid - l == 1) for (int k = 0; k < 3; ++k) { pmn[3 * order[l] + k] = lo[k]; pmx[3 * order[l] + k] = hi[k]; }
+        if (r - mid == 1) for (int k = 0; k < 3; ++k) { pmn[3 * order[mid] + k] = lo[k]; pmx[3 * order[mid] + k] = hi[k]; }
         split(l, mid);
         split(mid, r);
     }
@@ -258,8 +265,19 @@ int upload_and_build(pt_scene* s) {
     cudaStream_t st = s->stream;
     // device order = the reference's leaf visiting order, so that exact ties resolve by index (pt_wavefront.cuh)
     std::vector<uint32_t> rank(std::max(n, 1));
-    if (s->opt_tie_order && n >= 2) rank = RefOrder(s->prims).ranks();
-    else for (int i = 0; i < n; ++i) rank[i] = (uint32_t)i;
+    std::vector<float4> tb_mn, tb_mx;      // PT_OPT_REF_LEAF_BOXES: per device primitive, the reference parent's box
+    if ((s->opt_tie_order || s->opt_ref_leaf_boxes) && n >= 2) {
+        RefOrder ro(s->prims);
+        rank = ro.ranks();
+        if (!s->opt_tie_order) for (int i = 0; i < n; ++i) rank[i] = (uint32_t)i;
+        if (s->opt_ref_leaf_boxes) {
+            tb_mn.resize(n); tb_mx.resize(n);
+            for (int i = 0; i < n; ++i) {
+                tb_mn[rank[i]] = make_float4(ro.pmn[3 * i], ro.pmn[3 * i + 1], ro.pmn[3 * i + 2], 0.f);
+                tb_mx[rank[i]] = make_float4(ro.pmx[3 * i], ro.pmx[3 * i + 1], ro.pmx[3 * i + 2], 0.f);
+            }
+        }
+    } else for (int i = 0; i < n; ++i) rank[i] = (uint32_t)i;
     std::vector<float4> g0(std::max(n, 1)), g1(std::max(n, 1));
     std::vector<int> orig(std::max(n, 1));
     std::vector<float> py; std::vector<int> pid, tree;
@@ -295,6 +313,12 @@ int upload_and_build(pt_scene* s) {
         CK(cudaMemcpyAsync(s->plat_y.p, py.data(), py.size() * sizeof(float), cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(s->plat_id.p, pid.data(), pid.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     }
+    const bool use_tb = !tb_mn.empty();
+    if (use_tb) {
+        CK(s->test_mn.reserve(n)); CK(s->test_mx.reserve(n));
+        CK(cudaMemcpyAsync(s->test_mn.p, tb_mn.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(s->test_mx.p, tb_mx.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, st));
+    }
     s->n_plat = (int)py.size();
     s->n_tree = (int)tree.size();
     const int nt = s->n_tree;
@@ -309,7 +333,7 @@ int upload_and_build(pt_scene* s) {
             k_lbvh_single<<<1, 1, 0, st>>>(s->bvh_prims.p, s->geo0.p, s->geo1.p, s->nodes.p);
             s->stats.launches += 1;
         } else {
-            CK(s->leaf_mn.reserve(nt)); CK(s->leaf_mx.reserve(nt)); CK(s->inner_mn.reserve(nt)); CK(s->inner_mx.reserve(nt));
+            CK(s->leaf_mn.reserve(nt)); CK(s->leaf_mx.reserve(nt)); CK(s->leaf_c.reserve(nt)); CK(s->inner_mn.reserve(nt)); CK(s->inner_mx.reserve(nt));
             CK(s->codes.reserve(nt)); CK(s->codes_sorted.reserve(nt)); CK(s->ids.reserve(nt)); CK(s->ids_sorted.reserve(nt));
             CK(s->bounds6.reserve(8)); CK(s->children.reserve(nt)); CK(s->parent_inner.reserve(nt));
             CK(s->parent_leaf.reserve(nt)); CK(s->flags.reserve(nt));
@@ -317,8 +341,9 @@ int upload_and_build(pt_scene* s) {
             CK(cudaMemcpyAsync(s->bounds6.p, init6, sizeof(init6), cudaMemcpyHostToDevice, st));
             CK(cudaMemsetAsync(s->flags.p, 0, nt * sizeof(int), st));
             const int tb = 256, gb = (nt + tb - 1) / tb;
-            k_lbvh_bounds<<<gb, tb, 0, st>>>(nt, s->bvh_prims.p, s->geo0.p, s->geo1.p, s->leaf_mn.p, s->leaf_mx.p, s->bounds6.p);
-            k_lbvh_morton<<<gb, tb, 0, st>>>(nt, s->leaf_mn.p, s->leaf_mx.p, s->bounds6.p, s->codes.p, s->ids.p);
+            k_lbvh_bounds<<<gb, tb, 0, st>>>(nt, s->bvh_prims.p, s->geo0.p, s->geo1.p, use_tb ? s->test_mn.p : nullptr,
+                                             use_tb ? s->test_mx.p : nullptr, s->leaf_mn.p, s->leaf_mx.p, s->leaf_c.p, s->bounds6.p);
+            k_lbvh_morton<<<gb, tb, 0, st>>>(nt, s->leaf_c.p, s->bounds6.p, s->codes.p, s->ids.p);
             size_t tmp_bytes = 0;
             CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, s->codes.p, s->codes_sorted.p, s->ids.p, s->ids_sorted.p, nt, 0, 30, st));
             CK(s->cub_tmp.reserve(tmp_bytes + 16));
@@ -656,6 +681,7 @@ void pt_scene_destroy(pt_scene* s) {
     destroy_texture(s->sky);
     for (auto& kv : s->textures) destroy_texture(kv.second);
     s->geo0.release(); s->geo1.release(); s->nodes.release(); s->leaf_mn.release(); s->leaf_mx.release();
+    s->leaf_c.release(); s->test_mn.release(); s->test_mx.release();
     s->inner_mn.release(); s->inner_mx.release(); s->mats.release(); s->plat_y.release(); s->plat_id.release();
     s->bvh_prims.release(); s->parent_inner.release(); s->parent_leaf.release(); s->flags.release(); s->children.release();
     s->codes.release(); s->codes_sorted.release(); s->ids.release(); s->ids_sorted.release(); s->bounds6.release();
@@ -680,6 +706,7 @@ int pt_set_option(pt_scene* s, int option, int64_t value) {
         case PT_OPT_TIE_ORDER: s->opt_tie_order = value != 0; s->dirty = true; return PT_OK;
         case PT_OPT_SKY_QUARTER_ROWS: s->opt_sky_quarter = value != 0; return PT_OK;
         case PT_OPT_COUNT_STEPS: s->opt_count_steps = value != 0; return PT_OK;
+        case PT_OPT_REF_LEAF_BOXES: s->opt_ref_leaf_boxes = value != 0; s->dirty = true; return PT_OK;
         case PT_OPT_TRAV_INNER_RUN:
             if (value < 1 || value > 1024) return fail(PT_ERR_INVALID, "inner_run must be 1..1024");
             s->opt_inner_run = (int)value; return PT_OK;
@@ -831,7 +858,14 @@ int pt_trace_rays(pt_scene* s, int n, const float* rays8, int32_t* prim, float* 
     args.ctrl_in = s->ctrl.p; args.ctrl_out = s->ctrl.p + 1;
     args.ray_o = s->q_o.p; args.ray_d = s->q_d.p; args.ray_range = (const float2*)s->scratch_f[1].p; args.slot_hit = s->hit.p;
     args.n_rays = (uint32_t)n; args.step_counters = s->seg_counter.p + 1;
-    k_bounce<SRC_RAYS, false><<<s->grid_bounce, 32 * PT_BOUNCE_WARPS, 0, st>>>(args);
+    if (s->opt_count_steps) {
+        CK(s->scratch_i[1].reserve(n));
+        CK(cudaMemsetAsync(s->seg_counter.p, 0, 4 * sizeof(unsigned long long), st));
+        args.ray_steps = (uint32_t*)s->scratch_i[1].p;
+        k_bounce<SRC_RAYS, true><<<s->grid_bounce, 32 * PT_BOUNCE_WARPS, 0, st>>>(args);
+    } else {
+        k_bounce<SRC_RAYS, false><<<s->grid_bounce, 32 * PT_BOUNCE_WARPS, 0, st>>>(args);
+    }
     k_unpack_hits<<<g, 256, 0, st>>>(n, scene_dev(s), s->q_o.p, s->q_d.p, s->hit.p, s->scratch_i[0].p,
                                      s->scratch_f[2].p, s->scratch_f[3].p, s->scratch_f[4].p);
     s->stats.launches += 3;
@@ -841,6 +875,13 @@ int pt_trace_rays(pt_scene* s, int n, const float* rays8, int32_t* prim, float* 
     if (normal3) CK(cudaMemcpyAsync(normal3, s->scratch_f[3].p, (size_t)n * 12, cudaMemcpyDeviceToHost, st));
     if (hitpos3) CK(cudaMemcpyAsync(hitpos3, s->scratch_f[4].p, (size_t)n * 12, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    return PT_OK;
+}
+
+int pt_last_trace_steps(pt_scene* s, int n, uint32_t* steps) {
+    if (!s || !steps || n <= 0) return fail(PT_ERR_INVALID, "bad argument");
+    if (!s->opt_count_steps || s->scratch_i[1].n < (size_t)n) return fail(PT_ERR_INVALID, "needs PT_OPT_COUNT_STEPS and a previous pt_trace_rays of >= n rays");
+    CK(cudaMemcpy(steps, s->scratch_i[1].p, (size_t)n * 4, cudaMemcpyDeviceToHost));
     return PT_OK;
 }
 

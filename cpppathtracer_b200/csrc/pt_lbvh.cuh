@@ -57,18 +57,33 @@ __host__ __device__ __forceinline__ float ordered_to_float(uint32_t u) {
 }
 
 // pass 1: leaf boxes + scene bounds of the centroids.  bvh_prims[i] = primitive id of tree leaf slot i.
+// test_mn/test_mx (optional, PT_OPT_REF_LEAF_BOXES): the box that decides whether the primitive gets TESTED.  The
+// reference tests a leaf's object whenever the leaf's parent box is hit (bvh.cu:175-180), and far from the camera
+// its fp32 quadratics report hits on rays that miss the primitive's own box; with these boxes the walk tests the
+// same primitives the reference does (a finite platform-free parent box; primitives whose reference parent also
+// holds a platform keep their own box -- the platform's box is infinite).
 __global__ void k_lbvh_bounds(int n, const int* __restrict__ bvh_prims, const float4* __restrict__ geo0,
-                              const float4* __restrict__ geo1, float4* __restrict__ leaf_mn,
-                              float4* __restrict__ leaf_mx, uint32_t* __restrict__ bounds6) {
+                              const float4* __restrict__ geo1, const float4* __restrict__ test_mn,
+                              const float4* __restrict__ test_mx, float4* __restrict__ leaf_mn,
+                              float4* __restrict__ leaf_mx, float4* __restrict__ leaf_c, uint32_t* __restrict__ bounds6) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     float3 c = f3(0, 0, 0);
     bool valid = i < n;
     if (valid) {
         int p = bvh_prims[i];
         Aabb b = prim_aabb(geo0[p], geo1[p]);
+        c = f3(0.5f * (b.mn.x + b.mx.x), 0.5f * (b.mn.y + b.mx.y), 0.5f * (b.mn.z + b.mx.z));
+        if (test_mn != nullptr) {
+            const float4 tmn = test_mn[p], tmx = test_mx[p];
+            const bool finite = fabsf(tmn.x) < 1e29f && fabsf(tmx.x) < 1e29f && fabsf(tmn.z) < 1e29f && fabsf(tmx.z) < 1e29f;
+            if (finite) {
+                b.mn = f3(fminf(b.mn.x, ulp_out(tmn.x, -1.f)), fminf(b.mn.y, ulp_out(tmn.y, -1.f)), fminf(b.mn.z, ulp_out(tmn.z, -1.f)));
+                b.mx = f3(fmaxf(b.mx.x, ulp_out(tmx.x, 1.f)), fmaxf(b.mx.y, ulp_out(tmx.y, 1.f)), fmaxf(b.mx.z, ulp_out(tmx.z, 1.f)));
+            }
+        }
         leaf_mn[i] = make_float4(b.mn.x, b.mn.y, b.mn.z, 0.f);
         leaf_mx[i] = make_float4(b.mx.x, b.mx.y, b.mx.z, 0.f);
-        c = f3(0.5f * (b.mn.x + b.mx.x), 0.5f * (b.mn.y + b.mx.y), 0.5f * (b.mn.z + b.mx.z));
+        leaf_c[i] = make_float4(c.x, c.y, c.z, 0.f);     // Morton codes come from the primitive's own centre
     }
     // warp-reduce then one atomic per warp and component
     float mnx = valid ? c.x : 3e38f, mny = valid ? c.y : 3e38f, mnz = valid ? c.z : 3e38f;
@@ -95,20 +110,19 @@ __device__ __forceinline__ uint32_t expand_bits10(uint32_t v) {
 }
 
 // pass 2: 30-bit Morton code of the box centre on a cubic grid over the centroid bounds
-__global__ void k_lbvh_morton(int n, const float4* __restrict__ leaf_mn, const float4* __restrict__ leaf_mx,
-                              const uint32_t* __restrict__ bounds6, uint32_t* __restrict__ codes,
-                              uint32_t* __restrict__ ids) {
+__global__ void k_lbvh_morton(int n, const float4* __restrict__ leaf_c, const uint32_t* __restrict__ bounds6,
+                              uint32_t* __restrict__ codes, uint32_t* __restrict__ ids) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float3 lo = f3(ordered_to_float(bounds6[0]), ordered_to_float(bounds6[1]), ordered_to_float(bounds6[2]));
     float3 hi = f3(ordered_to_float(bounds6[3]), ordered_to_float(bounds6[4]), ordered_to_float(bounds6[5]));
-    float4 a = leaf_mn[i], b = leaf_mx[i];
+    const float4 c = leaf_c[i];
     // ONE scale for the three axes: the grid cells stay cubes.  Normalising each axis by its own extent makes the
     // code of a flat scene (spheres standing on a floor: y extent = radius spread) split on y as often as on x and
     // z, grouping primitives by radius instead of by position: SAH cost 25.9 vs 11.6 on C2, 71.8 vs 17.2 on a
     // 20 k-primitive field (2.0x / 3.4x fewer node visits per ray, profiles/r01_v4_summary.md).
     const float e = fmaxf(fmaxf(hi.x - lo.x, hi.y - lo.y), fmaxf(hi.z - lo.z, 1e-20f));
-    float x = (0.5f * (a.x + b.x) - lo.x) / e, y = (0.5f * (a.y + b.y) - lo.y) / e, z = (0.5f * (a.z + b.z) - lo.z) / e;
+    float x = (c.x - lo.x) / e, y = (c.y - lo.y) / e, z = (c.z - lo.z) / e;
     uint32_t xi = (uint32_t)fminf(fmaxf(x * 1024.f, 0.f), 1023.f);
     uint32_t yi = (uint32_t)fminf(fmaxf(y * 1024.f, 0.f), 1023.f);
     uint32_t zi = (uint32_t)fminf(fmaxf(z * 1024.f, 0.f), 1023.f);

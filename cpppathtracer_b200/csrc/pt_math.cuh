@@ -294,11 +294,14 @@ __device__ __forceinline__ void shade_bin(int bin, const MaterialRec& m, float3 
     }
 }
 
-// Miss, cuSrc/path_tracer.cu:117-122: the divisions by M_PI are double divisions
+// Miss, cuSrc/path_tracer.cu:117-122: the divisions by M_PI are DOUBLE divisions in the reference.  They are
+// evaluated here as double multiplications by 1/pi: the double results differ by <= 1 ulp(double), i.e. the float
+// they round to is the same except within 2^-29 of a rounding tie (and feeds an 8-bit-weight texture filter).
 __device__ __forceinline__ float3 sky_radiance(cudaTextureObject_t sky, float3 dir) {
     float3 d = normalize(dir);
-    float v = (float)((double)asinf(d.z) / PT_PI_D + 0.5);
-    float u = (float)((double)(atanf(d.y / d.x) / 2) / PT_PI_D);
+    const double inv_pi = 0.31830988618379067154;
+    float v = (float)((double)asinf(d.z) * inv_pi + 0.5);
+    float u = (float)((double)(atanf(d.y / d.x) / 2) * inv_pi);
     float4 t = tex2D<float4>(sky, u, v);
     return f3(t.x, t.y, t.z);
 }

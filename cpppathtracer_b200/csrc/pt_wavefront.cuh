@@ -195,6 +195,7 @@ struct BounceArgs {
     uint2* slot_hit;
     uint32_t n_rays;
     unsigned long long* step_counters;   // COUNT_STEPS: [0] inner nodes visited, [1] primitive tests
+    uint32_t* ray_steps;                 // COUNT_STEPS + SRC_RAYS: visits per ray (diagnostics)
 };
 
 template <int SRC, bool COUNT_STEPS>
@@ -307,18 +308,20 @@ __global__ void __launch_bounds__(32 * PT_BOUNCE_WARPS) k_bounce(const BounceArg
             }
             if (!a.trace) continue;
             // ================= 2. walk: while-while, the warp regroups between node runs and primitive tests =================
+            uint32_t lane_steps = 0;    // COUNT_STEPS: inner nodes + primitive tests of this lane's ray
             if (alive) { lane_begin(sc, r, stack); ++traced; }
             while (__any_sync(PT_FULL, alive && r.node != PT_SENTINEL)) {
                 if (alive) {
                     int k = 0;
 #pragma unroll 1
-                    while (r.node >= 0 && r.node != PT_SENTINEL && k < a.inner_run) { lane_inner(sc, r, stack); ++k; if (COUNT_STEPS) ++n_inner; }
+                    while (r.node >= 0 && r.node != PT_SENTINEL && k < a.inner_run) { lane_inner(sc, r, stack); ++k; if (COUNT_STEPS) { ++n_inner; ++lane_steps; } }
                 }
-                if (alive && r.node < 0) { lane_leaf(sc, r, stack); if (COUNT_STEPS) ++n_leaf; }
+                if (alive && r.node < 0) { lane_leaf(sc, r, stack); if (COUNT_STEPS) { ++n_leaf; ++lane_steps; } }
             }
             // ================= 3. file the results =================
             if (SRC == SRC_RAYS) {
                 if (alive) a.slot_hit[slot] = make_uint2(__float_as_uint(r.best_t), r.best_code);
+                if (COUNT_STEPS && alive && a.ray_steps != nullptr) a.ray_steps[slot] = lane_steps;
                 continue;
             }
             int obin = -1;

@@ -82,6 +82,9 @@ enum {
                                  visiting order (bvh.cu:31-90,167-205); 0: lowest primitive id wins */
     PT_OPT_SKY_QUARTER_ROWS = 4, /* 1 (default): reproduce the reference's upload that copies `width`
                                  BYTES per row (cuSrc/textures.cu:32); 0: upload whole rows         */
+    PT_OPT_REF_LEAF_BOXES = 9,  /* 1: a primitive is tested whenever the box of its PARENT in the reference's median-split
+                                   tree is hit, like SceneBVH::TraceRay does (bvh.cu:175-180); removes most of the
+                                   long-range graze-class differences at the price of more primitive tests. default 0 */
     PT_OPT_COUNT_STEPS = 8,     /* 1: use the instrumented traversal kernel that counts node visits / primitive tests */
     PT_OPT_TRAV_INNER_RUN = 7   /* tuning: inner-node steps a lane may take before the warp regroups for leaf tests */
 };
@@ -143,6 +146,8 @@ int pt_texture_destroy(pt_scene* s, uint64_t handle);
  *      rays8: n x (ox oy oz dx dy dz tmin tmax).  Outputs may be NULL. */
 /* closest hit (SceneBVH::TraceRay + Object::IntersectionTest, bvh.cu:167-205, object.cu:10-128) */
 int pt_trace_rays(pt_scene* s, int n, const float* rays8, int32_t* prim, float* t, float* normal3, float* hitpos3);
+/* diagnostics: BVH nodes + primitives visited by each ray of the last pt_trace_rays (needs PT_OPT_COUNT_STEPS) */
+int pt_last_trace_steps(pt_scene* s, int n, uint32_t* steps);
 /* Material::EvalAttenuationAndCreateRay with the uniforms given instead of drawn (material.cu:145-163) */
 int pt_shade_batch(pt_scene* s, int n, const pt_material* mats, int n_mats, const int32_t* mat_idx,
                    const float* pos3, const float* normal3, const float* in_dir3, const float* u3,

@@ -355,3 +355,57 @@ def test_level3_converged_image_1024spp(oracle, sky):
     gm, rm = img[..., :3].mean(axis=(0, 1)), ref.mean(axis=(0, 1))
     assert np.all(np.abs(gm - rm) <= 0.005 * rm)
     print(f"1024 spp: rmse {rmse:.3e}, means {gm} vs {rm}")
+
+
+def test_full_size_stress_scene_c3(oracle, port_oracle, sky):
+    """Config C3 at full size: 100 k mixed spheres / cylinders, glass-heavy, 1920x1080.  The oracle cannot render it in
+    seconds, so: closest-hit parity on a 150 k sample of its real camera / bounce rays, plus render properties."""
+    sc = scenes.stress_field(100000, 1920, 1080)
+    r = api.Renderer(sc, sky)
+    st0 = r.stats()
+    assert st0["bvh_nodes"] == sc.n_prims - 2            # every non-platform primitive is a leaf of the LBVH
+    oracle.load_scene(sc)
+    port_oracle.load_scene(sc)
+    small = scenes.Camera(480, 270, sc.camera.origin, sc.camera.look_at)
+    total, mism = 0, 0
+    for seg in (0, 1, 3):
+        rays, valid = port_oracle.segment_rays(small, seg, sample=seg, max_depth=8, seed=77)
+        rays = rays[valid][:50000]
+        m, exact = _check_trace(r, oracle, rays, max_mismatch_frac=1.5e-3)
+        total += len(rays); mism += m
+        assert exact > 0.999
+    # graze class (DESIGN.md section 4): the camera is ~1100 units away, where the reference's fp32 quadratics are
+    # coarse enough to report hits outside a primitive's own box and the winner depends on ITS traversal order.
+    # Measured 37 of 148 225 (2.5e-4); PT_OPT_REF_LEAF_BOXES (test the primitives the reference tests) brings it to 15
+    # at 41 % less throughput, which is why it is off by default.
+    assert mism <= 5e-4 * total, f"{mism} graze-class mismatches of {total}"
+    print(f"C3 graze-class mismatches: {mism} of {total}")
+    r2 = api.Renderer(); r2.set_option(api.PT_OPT_REF_LEAF_BOXES, 1); r2.load_scene(sc); r2.set_sky(sky); r2.build()
+    rays, valid = port_oracle.segment_rays(small, 0, sample=0, max_depth=8, seed=77)
+    rays = rays[valid][:50000]
+    m_on = int((r2.trace(rays)[0] != oracle.trace(rays)[0]).sum())
+    m_off = int((r.trace(rays)[0] != oracle.trace(rays)[0]).sum())
+    assert m_on <= m_off
+    r2.close()
+    r.render(sc.camera, 4, 8, seed=3); a = r.read_accum().copy()
+    st = r.stats()
+    assert 3.0 < st["segments"] / st["paths"] < 4.5      # glass-heavy: long paths (reference walk: 3.25 for spheres only)
+    r.reset_accum(); r.render(sc.camera, 4, 8, seed=3)
+    assert np.array_equal(a, r.read_accum())
+    assert np.isfinite(a).all()
+    r.close()
+
+
+def test_4k_frame_properties_c4(sky):
+    """Config C4 frame size (3840x2160): sample-range additivity is what spp-sharding across GPUs relies on."""
+    sc = scenes.sphere_field(1000, 3840, 2160)
+    r = api.Renderer(sc, sky)
+    r.render(sc.camera, 4, 8, seed=9); full = r.read_accum().copy()
+    r.reset_accum()
+    r.render(sc.camera, 2, 8, seed=9, first_sample=2)      # "rank 1" first: the SUM is order-dependent only in rounding
+    r.render(sc.camera, 2, 8, seed=9, first_sample=0)
+    split = r.read_accum()
+    assert (split[..., 3] == 4).all()
+    assert np.allclose(split[..., :3], full[..., :3], rtol=2e-6, atol=2e-6)
+    assert full.shape == (2160, 3840, 4) and np.isfinite(full).all()
+    r.close()
