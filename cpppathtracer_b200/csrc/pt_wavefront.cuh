@@ -69,7 +69,8 @@ struct LaneRay {
     float3 o, d;
     float ix, iy, iz;      // 1/d
     float ox, oy, oz;      // o/d, so that a slab plane distance is one FMA: plane*(1/d) - o/d
-    float slack;           // bound on the rounding error of those FMAs (added to the exit distance)
+    float slack;           // bound on the rounding error of those FMAs
+    float lo, hi;          // [tmin - slack, best_t (1 + 2^-21) + slack]: the interval a child box must overlap
     float tmin, best_t;
     uint32_t best_code;
     uint32_t slot;
@@ -97,6 +98,8 @@ __device__ __forceinline__ void lane_begin(const SceneDev& sc, LaneRay& r, int* 
     // |fma(p, 1/d, -o/d) - (p-o)/d| <= ~3 ulp of |o/d| (rounding of 1/d, of o/d and of the fma); culling only has
     // to be conservative, so both interval ends get that much slack (plus the 4-ulp inflation of the leaf boxes)
     r.slack = 4.0f * 1.1920929e-7f * fmaxf(fmaxf(fabsf(r.ox), fabsf(r.oy)), fabsf(r.oz));
+    r.lo = r.tmin - r.slack;
+    r.hi = r.best_t * 1.0000005f + r.slack;
     r.sp = 0;
     stack[r.sp++] = PT_SENTINEL;
     r.node = sc.n_tree_prims > 0 ? 0 : PT_SENTINEL;
@@ -125,7 +128,7 @@ __device__ __forceinline__ void lane_inner(const SceneDev& sc, LaneRay& r, int* 
         const float b0x = fmaf(n1.x, r.ix, -r.ox), b1x = fmaf(n1.y, r.ix, -r.ox);
         const float b0y = fmaf(n1.z, r.iy, -r.oy), b1y = fmaf(n1.w, r.iy, -r.oy);
         const float b0z = fmaf(n2.z, r.iz, -r.oz), b1z = fmaf(n2.w, r.iz, -r.oz);
-        const float lo = r.tmin - r.slack, hi = r.best_t * 1.0000005f + r.slack;
+        const float lo = r.lo, hi = r.hi;
         const float ea = fmaxf(fmaxf(fminf(a0x, a1x), fminf(a0y, a1y)), fmaxf(fminf(a0z, a1z), lo));
         const float xa = fminf(fminf(fmaxf(a0x, a1x), fmaxf(a0y, a1y)), fminf(fmaxf(a0z, a1z), hi));
         const float eb = fmaxf(fmaxf(fminf(b0x, b1x), fminf(b0y, b1y)), fmaxf(fminf(b0z, b1z), lo));
@@ -151,7 +154,7 @@ __device__ __forceinline__ void lane_leaf(const SceneDev& sc, LaneRay& r, int* s
         bool h;
         if ((leaf & 3u) == 2u) h = hit_cylinder(g0, __ldg(&sc.geo1[prim]).x, r.o, r.d, r.tmin, tm, part);
         else h = hit_sphere(g0, r.o, r.d, r.tmin, tm, part);
-        if (h) { r.best_t = tm; r.best_code = (prim << 3) | (uint32_t)part; }
+        if (h) { r.best_t = tm; r.best_code = (prim << 3) | (uint32_t)part; r.hi = tm * 1.0000005f + r.slack; }
         r.node = stack[--r.sp];
     }
 }
@@ -234,7 +237,7 @@ __global__ void __launch_bounds__(32 * PT_BOUNCE_WARPS) k_bounce(const BounceArg
             uint32_t pixel = 0, s = 0, slot = 0;
             LaneRay r;
             r.tmin = tmin; r.best_t = PT_TMAX; r.best_code = PT_MISS_CODE; r.node = PT_SENTINEL; r.sp = 0;
-            r.o = r.d = f3(0.f, 0.f, 0.f); r.ix = r.iy = r.iz = r.ox = r.oy = r.oz = r.slack = 0.f;
+            r.o = r.d = f3(0.f, 0.f, 0.f); r.ix = r.iy = r.iz = r.ox = r.oy = r.oz = r.slack = r.lo = r.hi = 0.f;
             if (SRC == SRC_CAMERA) {
                 const uint32_t pid = (chunk << 5) + lane;
                 if (pid < a.n_paths) {
@@ -265,10 +268,11 @@ __global__ void __launch_bounds__(32 * PT_BOUNCE_WARPS) k_bounce(const BounceArg
                 const uint32_t item = ((chunk - first_chunk) << 5) + lane;
                 if (item < n_bin) {
                     const size_t q = (size_t)bin * a.hq_in.capacity + item;
-                    const float4 o4 = a.hq_in.o[q];
-                    const float4 d4 = a.hq_in.d[q];
-                    const float4 t4 = a.hq_in.thr[q];
-                    const uint2 h = a.hq_in.hit[q];
+                    // streamed once: evict-first loads / stores keep the L1 and L2 lines for the BVH nodes
+                    const float4 o4 = __ldcs(&a.hq_in.o[q]);
+                    const float4 d4 = __ldcs(&a.hq_in.d[q]);
+                    const float4 t4 = __ldcs(&a.hq_in.thr[q]);
+                    const uint2 h = __ldcs(&a.hq_in.hit[q]);
                     pixel = __float_as_uint(o4.w);
                     s = __float_as_uint(d4.w);
                     const size_t pid = (size_t)s * a.npix + pixel;
@@ -337,10 +341,10 @@ __global__ void __launch_bounds__(32 * PT_BOUNCE_WARPS) k_bounce(const BounceArg
                     off = __shfl_sync(PT_FULL, off, leader);
                     if (obin == b) {
                         const size_t j = (size_t)b * a.hq_out.capacity + off + __popc(m & ((1u << lane) - 1u));
-                        a.hq_out.o[j] = make_float4(r.o.x, r.o.y, r.o.z, __uint_as_float(pixel));
-                        a.hq_out.d[j] = make_float4(r.d.x, r.d.y, r.d.z, __uint_as_float(s));
-                        a.hq_out.thr[j] = make_float4(thr.x, thr.y, thr.z, 0.f);
-                        a.hq_out.hit[j] = make_uint2(__float_as_uint(r.best_t), r.best_code);
+                        __stcs(&a.hq_out.o[j], make_float4(r.o.x, r.o.y, r.o.z, __uint_as_float(pixel)));
+                        __stcs(&a.hq_out.d[j], make_float4(r.d.x, r.d.y, r.d.z, __uint_as_float(s)));
+                        __stcs(&a.hq_out.thr[j], make_float4(thr.x, thr.y, thr.z, 0.f));
+                        __stcs(&a.hq_out.hit[j], make_uint2(__float_as_uint(r.best_t), r.best_code));
                     }
                 }
             }
