@@ -391,17 +391,35 @@ int ensure_frame(pt_scene* s, int w, int h) {
     return PT_OK;
 }
 
-int ensure_queues(pt_scene* s, uint32_t cap, int max_depth) {
-    if (cap > s->capacity) {
-        // released first so that growing never holds two copies
-        s->path_out.release();
-        for (int k = 0; k < 2; ++k) { s->hq_o[k].release(); s->hq_d[k].release(); s->hq_thr[k].release(); s->hq_hit[k].release(); }
-        CK(s->path_out.reserve(cap));
-        for (int k = 0; k < 2; ++k) {
-            CK(s->hq_o[k].reserve((size_t)NUM_BINS * cap)); CK(s->hq_d[k].reserve((size_t)NUM_BINS * cap));
-            CK(s->hq_thr[k].reserve((size_t)NUM_BINS * cap)); CK(s->hq_hit[k].reserve((size_t)NUM_BINS * cap));
-        }
-        s->capacity = cap;
+cudaError_t try_reserve_wave(pt_scene* s, uint32_t cap) {
+    if (cap <= s->capacity) return cudaSuccess;
+    // released first so that growing never holds two copies
+    s->path_out.release();
+    for (int k = 0; k < 2; ++k) { s->hq_o[k].release(); s->hq_d[k].release(); s->hq_thr[k].release(); s->hq_hit[k].release(); }
+    s->capacity = 0;
+    cudaError_t e = s->path_out.reserve(cap);
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+        e = s->hq_o[k].reserve((size_t)NUM_BINS * cap);
+        if (e == cudaSuccess) e = s->hq_d[k].reserve((size_t)NUM_BINS * cap);
+        if (e == cudaSuccess) e = s->hq_thr[k].reserve((size_t)NUM_BINS * cap);
+        if (e == cudaSuccess) e = s->hq_hit[k].reserve((size_t)NUM_BINS * cap);
+    }
+    if (e == cudaSuccess) { s->capacity = cap; return e; }
+    s->path_out.release();
+    for (int k = 0; k < 2; ++k) { s->hq_o[k].release(); s->hq_d[k].release(); s->hq_thr[k].release(); s->hq_hit[k].release(); }
+    cudaGetLastError();   // clear the sticky allocation error before the caller retries with a smaller wave
+    return e;
+}
+
+// Sizes the wave: as many samples per pixel as fit PT_OPT_WAVE_PATHS, halved until the hit queues fit in free
+// device memory (a 32 Mi-path wave reserves 19 GB; another tenant of the GPU must not make the frame fail).
+int ensure_queues(pt_scene* s, uint32_t npix, uint32_t& spp_per_wave, int max_depth) {
+    while (true) {
+        cudaError_t e = try_reserve_wave(s, npix * spp_per_wave);
+        if (e == cudaSuccess) break;
+        if (e != cudaErrorMemoryAllocation || spp_per_wave == 1)
+            return fail(PT_ERR_CUDA, std::string("wave queues: ") + cudaGetErrorString(e));
+        spp_per_wave = (spp_per_wave + 1) / 2;
     }
     CK(s->ctrl.reserve((size_t)max_depth + 3));
     CK(s->seg_counter.reserve(4));
@@ -438,8 +456,8 @@ int render_async(pt_scene* s, const pt_camera* cam, int spp, int max_depth, uint
     const uint32_t npix = (uint32_t)cam->width * (uint32_t)cam->height;
     uint32_t spp_per_wave = std::max<uint32_t>(1u, s->opt_wave_paths / npix);
     spp_per_wave = std::min<uint32_t>(spp_per_wave, (uint32_t)spp);
+    rc = ensure_queues(s, npix, spp_per_wave, max_depth); if (rc) return rc;
     const uint32_t cap = npix * spp_per_wave;
-    rc = ensure_queues(s, cap, max_depth); if (rc) return rc;
     cudaStream_t st = s->stream;
     const CameraFrame frame = to_device_frame(cam);
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
@@ -666,11 +684,17 @@ int pt_scene_create(pt_scene** out) {
     if (e != cudaSuccess || ndev == 0)
         return fail(PT_ERR_NO_DEVICE, std::string("no CUDA device (this library has no CPU path): ") + cudaGetErrorString(e));
     pt_scene* s = new pt_scene();
-    CK(cudaGetDevice(&s->device));
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, s->device));
-    s->sm_count = prop.multiProcessorCount;
-    CK(cudaEventCreate(&s->ev0)); CK(cudaEventCreate(&s->ev1));
+    int sms = 0;
+    e = cudaGetDevice(&s->device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
+    if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
+    if (e != cudaSuccess) {
+        if (s->ev0) cudaEventDestroy(s->ev0);
+        delete s;
+        return fail(PT_ERR_CUDA, std::string("pt_scene_create: ") + cudaGetErrorString(e));
+    }
+    s->sm_count = sms;
     *out = s;
     return PT_OK;
 }
