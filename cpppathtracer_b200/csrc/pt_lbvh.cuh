@@ -3,11 +3,13 @@
 // median-split build with a std::sort per level (SceneBVH::Divide, cuSrc/bvh.cu:31-90; 0.66 s for
 // 100 k objects) and its 112-byte AoS nodes that embed a copy of the Object (include/bvh.h:32-38).
 //
-// Node layout (64 B, four float4; both child boxes live in the parent so one fetch decides both):
-//   n0 = (c0.min.x, c0.max.x, c0.min.y, c0.max.y)
-//   n1 = (c1.min.x, c1.max.x, c1.min.y, c1.max.y)
-//   n2 = (c0.min.z, c0.max.z, c1.min.z, c1.max.z)
+// Node layout (64 B, four float4; both child boxes live in the parent so one fetch decides both).  Boxes are kept
+// as CENTRE + HALF-EXTENT: a slab pair is then  t_c = c*(1/d) - o/d,  near = t_c - h*|1/d|,  far = t_c + h*|1/d|
+// -- three FMAs and no min/max to sort the two plane distances (the walk is bound by the ALU pipe that executes
+// FMNMX; this moves 12 of its 28 operations per node to the FMA pipe, profiles/r01_v6_summary.md):
+//   n0 = (c0.x, c0.y, c0.z, h0.x)   n1 = (h0.y, h0.z, c1.x, c1.y)   n2 = (c1.z, h1.x, h1.y, h1.z)
 //   n3 = (bits child0, bits child1, -, -)       child >= 0: inner node index; child < 0: ~(prim<<2 | type)
+// h is rounded up by 4 ulp of (|c| + h) so that [c-h, c+h] contains the box after every rounding of the FMAs.
 // Platforms (infinite AABB, object.cu:141-142,160-161) are kept out of the tree in a side list.
 #pragma once
 #include <cub/cub.cuh>
@@ -191,6 +193,13 @@ __global__ void k_lbvh_fit(int n, const uint32_t* __restrict__ sorted_ids, const
     }
 }
 
+__device__ __forceinline__ void centre_half(float4 mn, float4 mx, float3& c, float3& h) {
+    c = f3(0.5f * (mn.x + mx.x), 0.5f * (mn.y + mx.y), 0.5f * (mn.z + mx.z));
+    h = f3(fmaxf(mx.x - c.x, c.x - mn.x), fmaxf(mx.y - c.y, c.y - mn.y), fmaxf(mx.z - c.z, c.z - mn.z));
+    h = f3(h.x + 4.8e-7f * (fabsf(c.x) + h.x) + 1e-30f, h.y + 4.8e-7f * (fabsf(c.y) + h.y) + 1e-30f,
+           h.z + 4.8e-7f * (fabsf(c.z) + h.z) + 1e-30f);
+}
+
 // pass 5: pack traversal nodes (child boxes in the parent, leaves as ~(prim<<2|type))
 __global__ void k_lbvh_pack(int n, const uint32_t* __restrict__ sorted_ids, const int* __restrict__ bvh_prims,
                             const float4* __restrict__ geo1, const float4* __restrict__ leaf_mn,
@@ -210,9 +219,12 @@ __global__ void k_lbvh_pack(int n, const uint32_t* __restrict__ sorted_ids, cons
         uint32_t s = sorted_ids[~ch.y]; bmn = leaf_mn[s]; bmx = leaf_mx[s];
         int p = bvh_prims[s]; c1 = ~((p << 2) | (__float_as_int(geo1[p].z) & 3));
     } else { bmn = inner_mn[ch.y]; bmx = inner_mx[ch.y]; c1 = ch.y; }
-    nodes[4 * i + 0] = make_float4(amn.x, amx.x, amn.y, amx.y);
-    nodes[4 * i + 1] = make_float4(bmn.x, bmx.x, bmn.y, bmx.y);
-    nodes[4 * i + 2] = make_float4(amn.z, amx.z, bmn.z, bmx.z);
+    float3 ca, ha, cb, hb;
+    centre_half(amn, amx, ca, ha);
+    centre_half(bmn, bmx, cb, hb);
+    nodes[4 * i + 0] = make_float4(ca.x, ca.y, ca.z, ha.x);
+    nodes[4 * i + 1] = make_float4(ha.y, ha.z, cb.x, cb.y);
+    nodes[4 * i + 2] = make_float4(cb.z, hb.x, hb.y, hb.z);
     nodes[4 * i + 3] = make_float4(__int_as_float(c0), __int_as_float(c1), 0.f, 0.f);
 }
 
@@ -222,9 +234,11 @@ __global__ void k_lbvh_single(const int* __restrict__ bvh_prims, const float4* _
     int p = bvh_prims[0];
     Aabb b = prim_aabb(geo0[p], geo1[p]);
     int c0 = ~((p << 2) | (__float_as_int(geo1[p].z) & 3));
-    nodes[0] = make_float4(b.mn.x, b.mx.x, b.mn.y, b.mx.y);
-    nodes[1] = make_float4(3e38f, -3e38f, 3e38f, -3e38f);
-    nodes[2] = make_float4(b.mn.z, b.mx.z, 3e38f, -3e38f);
+    float3 c, h;
+    centre_half(make_float4(b.mn.x, b.mn.y, b.mn.z, 0.f), make_float4(b.mx.x, b.mx.y, b.mx.z, 0.f), c, h);
+    nodes[0] = make_float4(c.x, c.y, c.z, h.x);
+    nodes[1] = make_float4(h.y, h.z, 0.f, 0.f);
+    nodes[2] = make_float4(0.f, -1.f, -1.f, -1.f);          // negative half-extent: near > far, never entered
     nodes[3] = make_float4(__int_as_float(c0), __int_as_float(c0), 0.f, 0.f);
 }
 

@@ -91,9 +91,10 @@ __device__ __forceinline__ void lane_begin(const SceneDev& sc, LaneRay& r, int* 
         float tm = tie_tmax(prim, r.best_t, r.best_code);
         if (hit_platform(sc.plat_y[k], r.o, r.d, r.tmin, tm)) { r.best_t = tm; r.best_code = (prim << 3) | PART_PLATFORM; }
     }
-    r.ix = 1.0f / (fabsf(r.d.x) > 1e-30f ? r.d.x : copysignf(1e-30f, r.d.x));
-    r.iy = 1.0f / (fabsf(r.d.y) > 1e-30f ? r.d.y : copysignf(1e-30f, r.d.y));
-    r.iz = 1.0f / (fabsf(r.d.z) > 1e-30f ? r.d.z : copysignf(1e-30f, r.d.z));
+    // |1/d| is capped at 1e18 so that c*(1/d) and h*|1/d| stay finite (no inf - inf) for coordinates up to 1e20
+    r.ix = 1.0f / (fabsf(r.d.x) > 1e-18f ? r.d.x : copysignf(1e-18f, r.d.x));
+    r.iy = 1.0f / (fabsf(r.d.y) > 1e-18f ? r.d.y : copysignf(1e-18f, r.d.y));
+    r.iz = 1.0f / (fabsf(r.d.z) > 1e-18f ? r.d.z : copysignf(1e-18f, r.d.z));
     r.ox = r.o.x * r.ix; r.oy = r.o.y * r.iy; r.oz = r.o.z * r.iz;
     // |fma(p, 1/d, -o/d) - (p-o)/d| <= ~3 ulp of |o/d| (rounding of 1/d, of o/d and of the fma); culling only has
     // to be conservative, so both interval ends get that much slack (plus the 4-ulp inflation of the leaf boxes)
@@ -122,17 +123,15 @@ __device__ __forceinline__ void lane_inner(const SceneDev& sc, LaneRay& r, int* 
     {
         float4 n0, n1, n2, n3;
         load_node(sc.nodes, r.node, n0, n1, n2, n3);
-        const float a0x = fmaf(n0.x, r.ix, -r.ox), a1x = fmaf(n0.y, r.ix, -r.ox);
-        const float a0y = fmaf(n0.z, r.iy, -r.oy), a1y = fmaf(n0.w, r.iy, -r.oy);
-        const float a0z = fmaf(n2.x, r.iz, -r.oz), a1z = fmaf(n2.y, r.iz, -r.oz);
-        const float b0x = fmaf(n1.x, r.ix, -r.ox), b1x = fmaf(n1.y, r.ix, -r.ox);
-        const float b0y = fmaf(n1.z, r.iy, -r.oy), b1y = fmaf(n1.w, r.iy, -r.oy);
-        const float b0z = fmaf(n2.z, r.iz, -r.oz), b1z = fmaf(n2.w, r.iz, -r.oz);
+        // child a: centre (n0.x n0.y n0.z), half (n0.w n1.x n1.y); child b: centre (n1.z n1.w n2.x), half (n2.y n2.z n2.w)
+        const float ax = fabsf(r.ix), ay = fabsf(r.iy), az = fabsf(r.iz);
+        const float tax = fmaf(n0.x, r.ix, -r.ox), tay = fmaf(n0.y, r.iy, -r.oy), taz = fmaf(n0.z, r.iz, -r.oz);
+        const float tbx = fmaf(n1.z, r.ix, -r.ox), tby = fmaf(n1.w, r.iy, -r.oy), tbz = fmaf(n2.x, r.iz, -r.oz);
         const float lo = r.lo, hi = r.hi;
-        const float ea = fmaxf(fmaxf(fminf(a0x, a1x), fminf(a0y, a1y)), fmaxf(fminf(a0z, a1z), lo));
-        const float xa = fminf(fminf(fmaxf(a0x, a1x), fmaxf(a0y, a1y)), fminf(fmaxf(a0z, a1z), hi));
-        const float eb = fmaxf(fmaxf(fminf(b0x, b1x), fminf(b0y, b1y)), fmaxf(fminf(b0z, b1z), lo));
-        const float xb = fminf(fminf(fmaxf(b0x, b1x), fmaxf(b0y, b1y)), fminf(fmaxf(b0z, b1z), hi));
+        const float ea = fmaxf(fmaxf(fmaf(-n0.w, ax, tax), fmaf(-n1.x, ay, tay)), fmaxf(fmaf(-n1.y, az, taz), lo));
+        const float xa = fminf(fminf(fmaf(n0.w, ax, tax), fmaf(n1.x, ay, tay)), fminf(fmaf(n1.y, az, taz), hi));
+        const float eb = fmaxf(fmaxf(fmaf(-n2.y, ax, tbx), fmaf(-n2.z, ay, tby)), fmaxf(fmaf(-n2.w, az, tbz), lo));
+        const float xb = fminf(fminf(fmaf(n2.y, ax, tbx), fmaf(n2.z, ay, tby)), fminf(fmaf(n2.w, az, tbz), hi));
         const bool ha = ea <= xa, hb = eb <= xb;
         const int ca = __float_as_int(n3.x), cb = __float_as_int(n3.y);
         if (ha && hb) {
