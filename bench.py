@@ -54,12 +54,13 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines = index, None, []   # lines: (arrival time, text)
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -68,7 +69,13 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self) -> dict:
         if self.proc is None:
@@ -80,7 +87,10 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        # nvidia-smi needs a few hundred ms to start, so it is launched before the warm-up; only the samples that
+        # arrived inside the marked (timed) region count
+        inside = [ln for (t, ln) in self.lines if self.t0 is not None and self.t0 <= t <= (self.t1 or t) + 0.06]
+        for ln in inside:
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 6:
                 continue
@@ -228,26 +238,28 @@ def main():
         if world > 1:
             ptd.reduce_sum_to_root(ptd.accum_tensor(r))
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(warmup):
         step()
     r.synchronize()
     launches0 = r.stats()["launches"]
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.mark_begin()
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     torch.cuda.synchronize()
+    sampler.mark_end()
     if world > 1:
         dist.barrier()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = None
     r.synchronize()
     st = r.stats()
     launches = st["launches"] - launches0
@@ -292,6 +304,16 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = paths_per_step * e2e_steps / float(te.item()) / 1e6
+    if rank == 0:
+        clocks = sampler.stop()
+        if not clocks.get("samples"):
+            # the timed region was shorter than one sampling period: use the samples of the e2e leg (same workload,
+            # same kernels, back to back) and say so
+            sampler.t1 = time.perf_counter()
+            clocks = sampler.stop()
+            clocks["window"] = "timed region + e2e leg"
+        else:
+            clocks["window"] = "timed region"
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -317,9 +339,9 @@ def main():
                          "algorithmic_bytes_per_launch": alg_bytes / n_launch, "avg_launch_ms": kern_ms / n_launch,
                          "launches_per_step": n_launch,
                          "share_of_step": kern_ms / st["render_ms"] if st["render_ms"] > 0 else None,
-                         "note": "the kernel is bound by instruction issue / the ALU pipe (IPC 2.5-3.1 of 4, ALU pipe 51-67 %, "
-                                 "17-27 of 32 lanes active, profiles/r01_v5_summary.md), not by HBM; DRAM traffic equals the "
-                                 "algorithmic bytes (ratio 1.006)"},
+                         "note": "bound by instruction issue x SIMD efficiency (IPC 2.4-3.2 of 4, 17-27 of 32 lanes active, "
+                                 "long-scoreboard on L1/L2 node fetches; profiles/r01_v6_summary.md), not by HBM; DRAM traffic "
+                                 "equals the algorithmic bytes (ratio 1.02)"},
             "path": {"mrays_per_s": segs / (st["render_ms"] * 1e-3) / 1e6 if st["render_ms"] > 0 else None,
                      "segments_per_path": segs / st["paths"], "render_ms_last_frame": st["render_ms"],
                      "bounce_kernel_ms": kern_ms,
