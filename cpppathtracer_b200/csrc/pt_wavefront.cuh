@@ -137,7 +137,10 @@ __device__ __forceinline__ void lane_inner(const SceneDev& sc, LaneRay& r, int* 
         if (ha && hb) {
             const bool a_near = ea <= eb;
             r.node = a_near ? ca : cb;
-            stack[r.sp++] = a_near ? cb : ca;
+            const int far = a_near ? cb : ca;
+            stack[r.sp++] = far;
+            // the far child is visited later (if at all): start pulling its node towards L1 now
+            if (far >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(sc.nodes + 4 * (size_t)far));
         } else if (ha) r.node = ca;
         else if (hb) r.node = cb;
         else r.node = stack[--r.sp];
