@@ -44,7 +44,7 @@ EXPORTS = [
     "pt_get_stats", "pt_dispatch_ray", "pt_texture_create_rgba8", "pt_texture_destroy", "pt_trace_rays", "pt_last_trace_steps",
     "pt_shade_batch", "pt_raygen_batch", "pt_sky_lookup", "pt_philox_uniforms", "pt_camera_basis", "pt_camera_control",
     "pt_last_error",
-    "pt_version",
+    "pt_version", "pt_image_load_png", "pt_image_free",
 ]
 
 
@@ -113,6 +113,20 @@ def to_pt_material(m, tex: int = 0) -> PtMaterial:
     r.refractive_index = float(m["refractive_index"]); r.emit_intensity = float(m["emit_intensity"])
     r.smoothness = float(m["smoothness"]); r.reflectivity = float(m["reflectivity"]); r.tex = int(tex)
     return r
+
+
+def load_png(path: str) -> np.ndarray:
+    """RGBA8 [H,W,4] from an 8-bit PNG file (host only; the reference used cv::imread, textures.cu:15-17)."""
+    lib = load_library()
+    p = C.POINTER(C.c_uint8)(); w = C.c_int(); h = C.c_int()
+    lib.pt_image_load_png.argtypes = [C.c_char_p, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.pt_image_free.argtypes = [C.POINTER(C.c_uint8)]
+    lib.pt_image_free.restype = None
+    if lib.pt_image_load_png(path.encode(), C.byref(p), C.byref(w), C.byref(h)):
+        raise PtError(lib.pt_last_error().decode())
+    out = np.ctypeslib.as_array(p, shape=(h.value, w.value, 4)).copy()
+    lib.pt_image_free(p)
+    return out
 
 
 def camera_basis(cam) -> np.ndarray:

@@ -675,6 +675,7 @@ int display_dispatch(pt_scene* s, const pt_camera* cam, int max_depth, uint64_t 
 extern "C" {
 
 const char* pt_last_error(void) { return g_err.c_str(); }
+int pt_set_error_text(const char* msg) { g_err = msg ? msg : ""; return 0; }   // for the other translation units of the library
 const char* pt_version(void) { return "cpppathtracer_b200 0.1 (sm_100a wavefront)"; }
 
 int pt_scene_create(pt_scene** out) {

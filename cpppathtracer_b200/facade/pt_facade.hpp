@@ -256,9 +256,16 @@ public:
         fclose(f);
         return ok;
     }
-    static unsigned long long AddTexByFile(pt_scene* scene, const std::string& ppm_path) {
-        std::vector<uint8_t> rgba; int w = 0, h = 0;
-        if (!ReadPpm(ppm_path, rgba, w, h)) return 0ull;
+    // PocaTextureUtils::AddTexByFile (cuSrc/textures.cu:14-62): PNG through the library's reader, PPM as a fallback
+    static unsigned long long AddTexByFile(pt_scene* scene, const std::string& path) {
+        uint8_t* px = nullptr; int w = 0, h = 0;
+        if (pt_image_load_png(path.c_str(), &px, &w, &h) == PT_OK) {
+            unsigned long long t = AddTexByRgba8(scene, px, w, h);
+            pt_image_free(px);
+            return t;
+        }
+        std::vector<uint8_t> rgba;
+        if (!ReadPpm(path, rgba, w, h)) return 0ull;
         return AddTexByRgba8(scene, rgba.data(), w, h);
     }
     static void DestroyTexture(pt_scene* scene, unsigned long long tex) { pt_texture_destroy(scene, (uint64_t)tex); }
@@ -359,6 +366,14 @@ public:
 
     // additions (no counterpart in the reference)
     bool SetSkyRgba8(const uint8_t* rgba, int w, int h) { return scene_ && pt_set_sky_rgba8(scene_, rgba, w, h) == PT_OK; }
+    // the reference loads "textures\\sky.png" itself (path_tracer.cu:47); here the caller names the file
+    bool SetSkyFile(const std::string& png_path) {
+        uint8_t* px = nullptr; int w = 0, h = 0;
+        if (!scene_ || pt_image_load_png(png_path.c_str(), &px, &w, &h) != PT_OK) { err_ = pt_last_error(); return false; }
+        const bool ok = pt_set_sky_rgba8(scene_, px, w, h) == PT_OK;
+        pt_image_free(px);
+        return ok;
+    }
     void SetSeed(uint64_t seed) { seed_ = seed; }
     pt_scene* Handle() { return scene_; }
     const std::string& LastError() const { return err_; }

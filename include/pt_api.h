@@ -142,6 +142,11 @@ int pt_dispatch_ray(pt_scene* s, const pt_camera* cam, int max_depth, uint64_t s
 int pt_texture_create_rgba8(pt_scene* s, const uint8_t* rgba, int width, int height, uint64_t* handle);
 int pt_texture_destroy(pt_scene* s, uint64_t handle);
 
+/* ---- image files: replaces cv::imread + cvtColor(CV_BGR2RGBA) of AddTexByFile (cuSrc/textures.cu:15-17).
+ *      8-bit non-interlaced PNG (grey, grey+alpha, RGB, RGBA, palette) -> malloc'ed RGBA8 rows; host only. */
+int pt_image_load_png(const char* path, uint8_t** rgba_out, int* width, int* height);
+void pt_image_free(uint8_t* rgba);
+
 /* ---- parity entry points: the SAME device code as the render path, on caller-supplied batches.
  *      rays8: n x (ox oy oz dx dy dz tmin tmax).  Outputs may be NULL. */
 /* closest hit (SceneBVH::TraceRay + Object::IntersectionTest, bvh.cu:167-205, object.cu:10-128) */

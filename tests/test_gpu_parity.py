@@ -409,3 +409,25 @@ def test_4k_frame_properties_c4(sky):
     assert np.allclose(split[..., :3], full[..., :3], rtol=2e-6, atol=2e-6)
     assert full.shape == (2160, 3840, 4) and np.isfinite(full).all()
     r.close()
+
+
+def test_material_texture_is_sampled_at_origin(sky):
+    """Material::GetKd with have_tex_ (material.cu:11-18): the reference samples the texture at (0,0) for every hit
+    (no UVs exist), so a constant-colour texture must render exactly like kd = that colour, and the attenuation of a
+    non-constant texture is its texel (0,0) under the linear / mirror sampler."""
+    sc = scenes.demo_scene(160, 90)
+    col = np.array([200, 120, 40], np.uint8)
+    r1 = api.Renderer(); r2 = api.Renderer()
+    tex = r1.create_texture(np.tile(np.append(col, 255).astype(np.uint8), (8, 8, 1)))
+    for r, use_tex in ((r1, True), (r2, False)):
+        r.add_platform(0.0)
+        m = scenes.np.zeros(1, scenes.MATERIAL_DTYPE)[0]
+        m["type"] = scenes.DIFFUSE; m["kd"] = tuple(col.astype(np.float32) / np.float32(255))
+        r.set_material(0, api.to_pt_material(m, tex=tex if use_tex else 0))
+        p = r.add_sphere((0, 20, 0), 20.0)
+        r.set_material(p, api.to_pt_material(sc.materials[0]))
+        r.set_sky(sky); r.build()
+        r.render(sc.camera, 8, 8, seed=4)
+    a, b = r1.read_accum(), r2.read_accum()
+    assert np.abs(a[..., :3] - b[..., :3]).max() < 1e-6 and a[..., :3].mean() > 0.05
+    r1.close(); r2.close()

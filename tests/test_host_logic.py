@@ -122,3 +122,30 @@ def test_video_camera_path_and_moving_objects():
     ids2, c2 = video.moving_spheres(sc, 4)
     assert np.array_equal(ids, ids2) and len(ids) == 10 and not np.array_equal(c, c2)
     assert (c[:, 1] >= sc.radius[ids] - 1e-6).all()
+
+
+def test_png_loader_matches_pil(tmp_path):
+    """pt_image_load_png (replaces cv::imread + BGR2RGBA of textures.cu:15-17) against PIL on every supported layout."""
+    from PIL import Image
+    rng = np.random.RandomState(5)
+    h, w = 37, 53
+    rgb = rng.randint(0, 256, (h, w, 3)).astype(np.uint8)
+    rgb[:, : w // 2] = (np.linspace(0, 255, h)[:, None, None] * np.ones((1, w // 2, 3))).astype(np.uint8)   # smooth half: exercises the filters
+    rgba = np.dstack([rgb, rng.randint(0, 256, (h, w, 1)).astype(np.uint8)])
+    images = {"rgb": Image.fromarray(rgb, "RGB"), "rgba": Image.fromarray(rgba, "RGBA"), "grey": Image.fromarray(rgb[..., 0], "L"),
+              "la": Image.fromarray(rgba[..., [0, 3]], "LA"), "pal": Image.fromarray(rgb, "RGB").quantize(64)}
+    for name, im in images.items():
+        path = str(tmp_path / f"{name}.png")
+        im.save(path, optimize=(name == "rgb"))
+        got = api.load_png(path)
+        want = np.array(Image.open(path).convert("RGBA"))
+        assert got.shape == (h, w, 4) and np.array_equal(got, want), name
+    bad = tmp_path / "bad.png"
+    bad.write_bytes(b"not a png at all" * 4)
+    with pytest.raises(api.PtError):
+        api.load_png(str(bad))
+    Image.fromarray((rng.rand(8, 8) * 65535).astype(np.uint16)).save(str(tmp_path / "deep.png"))
+    with pytest.raises(api.PtError):
+        api.load_png(str(tmp_path / "deep.png"))
+    with pytest.raises(api.PtError):
+        api.load_png(str(tmp_path / "missing.png"))
