@@ -61,6 +61,9 @@ struct SceneDev {
 // on the floor plane (video_renderer.cpp:78,105-106).  Device primitive indices ARE the reference's leaf
 // visiting order (upload_and_build in pt_api.cu), so a tied candidate wins iff its index is lower than the
 // current holder's: the intersector is then handed a tmax one ulp above best_t, so its `t < tmax` admits t == best_t.
+#ifndef PT_BOUNCE_MIN_BLOCKS
+#define PT_BOUNCE_MIN_BLOCKS 10   // 48 registers (60 B of spills): +1 % on C2, +3 % on C3 over 56 registers / 9 CTAs
+#endif
 #ifndef PT_BOUNCE_WARPS
 #define PT_BOUNCE_WARPS 4
 #endif
@@ -204,7 +207,7 @@ struct BounceArgs {
 };
 
 template <int SRC, bool COUNT_STEPS>
-__global__ void __launch_bounds__(32 * PT_BOUNCE_WARPS) k_bounce(const BounceArgs a) {
+__global__ void __launch_bounds__(32 * PT_BOUNCE_WARPS, PT_BOUNCE_MIN_BLOCKS) k_bounce(const BounceArgs a) {
     const uint32_t lane = threadIdx.x & 31u;
     const SceneDev& sc = a.sc;
     // ---- work list: 32-item chunks; SRC_HITS chunks never straddle two shader bins ----
