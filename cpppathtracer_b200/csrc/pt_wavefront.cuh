@@ -62,7 +62,7 @@ struct SceneDev {
 // visiting order (upload_and_build in pt_api.cu), so a tied candidate wins iff its index is lower than the
 // current holder's: the intersector is then handed a tmax one ulp above best_t, so its `t < tmax` admits t == best_t.
 #ifndef PT_BOUNCE_MIN_BLOCKS
-#define PT_BOUNCE_MIN_BLOCKS 10   // 48 registers (60 B of spills): +1 % on C2, +3 % on C3 over 56 registers / 9 CTAs
+#define PT_BOUNCE_MIN_BLOCKS 0   // 0: let ptxas choose (56 registers, 9 CTAs/SM). Same-box A/B: forcing 10 CTAs (48 regs) is 3 % slower on C2
 #endif
 #ifndef PT_BOUNCE_WARPS
 #define PT_BOUNCE_WARPS 4
@@ -206,8 +206,13 @@ struct BounceArgs {
     uint32_t* ray_steps;                 // COUNT_STEPS + SRC_RAYS: visits per ray (diagnostics)
 };
 
+#if PT_BOUNCE_MIN_BLOCKS > 0
+#define PT_BOUNCE_BOUNDS __launch_bounds__(32 * PT_BOUNCE_WARPS, PT_BOUNCE_MIN_BLOCKS)
+#else
+#define PT_BOUNCE_BOUNDS __launch_bounds__(32 * PT_BOUNCE_WARPS)
+#endif
 template <int SRC, bool COUNT_STEPS>
-__global__ void __launch_bounds__(32 * PT_BOUNCE_WARPS, PT_BOUNCE_MIN_BLOCKS) k_bounce(const BounceArgs a) {
+__global__ void PT_BOUNCE_BOUNDS k_bounce(const BounceArgs a) {
     const uint32_t lane = threadIdx.x & 31u;
     const SceneDev& sc = a.sc;
     // ---- work list: 32-item chunks; SRC_HITS chunks never straddle two shader bins ----
