@@ -206,6 +206,55 @@ struct BounceArgs {
     uint32_t* ray_steps;                 // COUNT_STEPS + SRC_RAYS: visits per ray (diagnostics)
 };
 
+// Shade (or miss) item `item` of shader bin `bin` of the input hit queue.  Returns true and the next ray when the
+// path goes on; paths that end write their radiance.
+__device__ __forceinline__ bool shade_hit_item(const BounceArgs& a, int bin, uint32_t item, bool last_shade, float3& ray_o,
+                                               float3& ray_d, float3& thr, uint32_t& pixel, uint32_t& s) {
+    const SceneDev& sc = a.sc;
+    const size_t q = (size_t)bin * a.hq_in.capacity + item;
+    // streamed once: evict-first loads / stores keep the L1 and L2 lines for the BVH nodes
+    const float4 o4 = __ldcs(&a.hq_in.o[q]);
+    const float4 d4 = __ldcs(&a.hq_in.d[q]);
+    const float4 t4 = __ldcs(&a.hq_in.thr[q]);
+    const uint2 h = __ldcs(&a.hq_in.hit[q]);
+    pixel = __float_as_uint(o4.w);
+    s = __float_as_uint(d4.w);
+    const size_t pid = (size_t)s * a.npix + pixel;
+    const float3 o = f3(o4.x, o4.y, o4.z), d = f3(d4.x, d4.y, d4.z);
+    thr = f3(t4.x, t4.y, t4.z);
+    if (bin == BIN_MISS) {
+        // Miss, path_tracer.cu:117-122: the path ends with the sky seen through its throughput
+        const float3 c = thr * sky_radiance(sc.sky, d);
+        if (sc.has_emitters) { float4 p = a.path_out[pid]; a.path_out[pid] = make_float4(p.x + c.x, p.y + c.y, p.z + c.z, 0.f); }
+        else a.path_out[pid] = make_float4(c.x, c.y, c.z, 0.f);
+        // G-buffer of the display pipeline: a first-segment miss records -dir (path_tracer.cu:152)
+        if (a.gbuf_normal != nullptr && a.segment == 1) a.gbuf_normal[pid] = make_float4(-d.x, -d.y, -d.z, 0.f);
+        return false;
+    }
+    const uint32_t prim = h.y >> 3;
+    const float4 g0 = __ldg(&sc.geo0[prim]);
+    const uint32_t mslot = __float_as_uint(__ldg(&sc.geo1[prim]).w) & 0x0fffffffu;
+    const MaterialRec m = sc.mats[mslot];
+    float3 pos, normal;
+    hit_attributes(g0, (int)(h.y & 7u), o, d, __uint_as_float(h.x), pos, normal);
+    if (a.gbuf_normal != nullptr && a.segment == 1) a.gbuf_normal[pid] = make_float4(normal.x, normal.y, normal.z, 0.f);
+    const float4 U = philox_uniform4(a.key, pixel, a.first_sample + s, (uint32_t)a.segment);   // slot 1 + (k-1)
+    Scatter sct;
+    shade_bin(bin, m, normal, d, U, sct);
+    if (sc.has_emitters) {
+        const float3 c = thr * sct.radiance;
+        float4 p = a.path_out[pid];
+        a.path_out[pid] = make_float4(p.x + c.x, p.y + c.y, p.z + c.z, 0.f);
+    }
+    thr = thr * sct.atten;
+    // a path whose throughput is exactly zero can add nothing more (finite sky and emission): ending it here is
+    // result-identical to the reference, which keeps bouncing it (path_tracer.cu:141-170)
+    const bool alive = !last_shade && (thr.x != 0.f || thr.y != 0.f || thr.z != 0.f);
+    if (!alive && !sc.has_emitters) a.path_out[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (alive) { ray_o = pos; ray_d = normalize(sct.bounce); }
+    return alive;
+}
+
 #if PT_BOUNCE_MIN_BLOCKS > 0
 #define PT_BOUNCE_BOUNDS __launch_bounds__(32 * PT_BOUNCE_WARPS, PT_BOUNCE_MIN_BLOCKS)
 #else
@@ -276,49 +325,7 @@ __global__ void PT_BOUNCE_BOUNDS k_bounce(const BounceArgs a) {
                 for (int b = 1; b < NUM_BINS; ++b)
                     if (chunk >= chunk_end[b - 1]) { bin = b; first_chunk = chunk_end[b - 1]; n_bin = bin_n[b]; }
                 const uint32_t item = ((chunk - first_chunk) << 5) + lane;
-                if (item < n_bin) {
-                    const size_t q = (size_t)bin * a.hq_in.capacity + item;
-                    // streamed once: evict-first loads / stores keep the L1 and L2 lines for the BVH nodes
-                    const float4 o4 = __ldcs(&a.hq_in.o[q]);
-                    const float4 d4 = __ldcs(&a.hq_in.d[q]);
-                    const float4 t4 = __ldcs(&a.hq_in.thr[q]);
-                    const uint2 h = __ldcs(&a.hq_in.hit[q]);
-                    pixel = __float_as_uint(o4.w);
-                    s = __float_as_uint(d4.w);
-                    const size_t pid = (size_t)s * a.npix + pixel;
-                    const float3 o = f3(o4.x, o4.y, o4.z), d = f3(d4.x, d4.y, d4.z);
-                    thr = f3(t4.x, t4.y, t4.z);
-                    if (bin == BIN_MISS) {
-                        // Miss, path_tracer.cu:117-122: the path ends with the sky seen through its throughput
-                        const float3 c = thr * sky_radiance(sc.sky, d);
-                        if (sc.has_emitters) { float4 p = a.path_out[pid]; a.path_out[pid] = make_float4(p.x + c.x, p.y + c.y, p.z + c.z, 0.f); }
-                        else a.path_out[pid] = make_float4(c.x, c.y, c.z, 0.f);
-                        // G-buffer of the display pipeline: a first-segment miss records -dir (path_tracer.cu:152)
-                        if (a.gbuf_normal != nullptr && a.segment == 1) a.gbuf_normal[pid] = make_float4(-d.x, -d.y, -d.z, 0.f);
-                    } else {
-                        const uint32_t prim = h.y >> 3;
-                        const float4 g0 = __ldg(&sc.geo0[prim]);
-                        const uint32_t mslot = __float_as_uint(__ldg(&sc.geo1[prim]).w) & 0x0fffffffu;
-                        const MaterialRec m = sc.mats[mslot];
-                        float3 pos, normal;
-                        hit_attributes(g0, (int)(h.y & 7u), o, d, __uint_as_float(h.x), pos, normal);
-                        if (a.gbuf_normal != nullptr && a.segment == 1) a.gbuf_normal[pid] = make_float4(normal.x, normal.y, normal.z, 0.f);
-                        const float4 U = philox_uniform4(a.key, pixel, a.first_sample + s, (uint32_t)a.segment);   // slot 1 + (k-1)
-                        Scatter sct;
-                        shade_bin(bin, m, normal, d, U, sct);
-                        if (sc.has_emitters) {
-                            const float3 c = thr * sct.radiance;
-                            float4 p = a.path_out[pid];
-                            a.path_out[pid] = make_float4(p.x + c.x, p.y + c.y, p.z + c.z, 0.f);
-                        }
-                        thr = thr * sct.atten;
-                        // a path whose throughput is exactly zero can add nothing more (finite sky and emission): ending it
-                        // here is result-identical to the reference, which keeps bouncing it (path_tracer.cu:141-170)
-                        alive = !last_shade && (thr.x != 0.f || thr.y != 0.f || thr.z != 0.f);
-                        if (!alive && !sc.has_emitters) a.path_out[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (alive) { r.o = pos; r.d = normalize(sct.bounce); }
-                    }
-                }
+                if (item < n_bin) alive = shade_hit_item(a, bin, item, last_shade, r.o, r.d, thr, pixel, s);
             }
             if (!a.trace) continue;
             // ================= 2. walk: while-while, the warp regroups between node runs and primitive tests =================
