@@ -1,0 +1,26 @@
+"""Display path throughput: pt_dispatch_ray (1 spp + Denoising + Mix + BGRA8 + D2H per call) at 1080p on C2, next to the
+reference's own per-sample service loop (SamplePixel + Denoising + Mix + 3 syncs + D2H) rebuilt for sm_100."""
+import os, sys, time, json
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from cpppathtracer_b200 import api, scenes
+sc = scenes.sphere_field(1000, 1920, 1080)
+sky = scenes.synthetic_sky(1280, 1280)
+r = api.Renderer(sc, sky)
+for i in range(1, 6):
+    r.dispatch_ray(sc.camera, i)
+n = 60
+t0 = time.perf_counter()
+for i in range(6, 6 + n):
+    r.dispatch_ray(sc.camera, i)
+dt = time.perf_counter() - t0
+out = {"dispatch_ms": dt / n * 1e3, "mpaths_per_s": 1920 * 1080 * n / dt / 1e6}
+try:
+    from oracle import ref_cuda
+    R = ref_cuda.RefCuda(); R.load_scene(sc); R.set_sky(sky)
+    o = R.render(sc.camera, 16, warmup=2)
+    out["reference_service_loop_mpaths_per_s"] = o["mpaths_service"]
+    out["reference_service_ms_per_sample"] = o["service_ms"] / 16
+except Exception as e:
+    out["reference"] = str(e)
+print(json.dumps(out))
