@@ -167,6 +167,20 @@ def reference_arm(args, out):
         "gpu_launches": 0})])
 
 
+def fma_variant_leg(sc, sky):
+    """Same workload through libpt_b200_fma.so (reported beside the headline, which is the default library's)."""
+    from cpppathtracer_b200 import api
+    if not os.path.exists(api.LIB_PATH_FMA):
+        return None
+    r = api.Renderer(sc, sky, lib_path=api.LIB_PATH_FMA)
+    for _ in range(3):
+        r.reset_accum()
+        r.render(sc.camera, WORKLOAD["spp"], WORKLOAD["max_depth"], seed=2026)
+    st = r.stats()
+    r.close()
+    return {"value": st["paths"] / st["render_ms"] / 1e3, "unit": "Mpaths/s", "how": "device time of one 64-spp frame (CUDA events), third of three"}
+
+
 def ref_cuda_leg(sc, sky):
     """Reported baseline (north_star): the reference's own CUDA kernels rebuilt for sm_100, same scene."""
     try:
@@ -352,6 +366,7 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if world == 1 and not args.no_baselines:
+            line["variants"] = {"libpt_b200_fma.so (nvcc-contracted arithmetic of the reference's CUDA build)": fma_variant_leg(sc, sky)}
             line["cpu_baseline"] = cpu_baseline_leg(sc, sky)
             rc = ref_cuda_leg(sc, sky)
             if rc is not None:

@@ -13,7 +13,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpt_b200.so")
+LIB_PATH = os.path.join(_HERE, "libpt_b200.so")          # default: uncontracted arithmetic == the CPU oracle's
+LIB_PATH_FMA = os.path.join(_HERE, "libpt_b200_fma.so")  # nvcc-contracted arithmetic == the reference's CUDA build
 
 PT_OPT_WAVE_PATHS, PT_OPT_STAGE_TIMING, PT_OPT_TIE_ORDER, PT_OPT_SKY_QUARTER_ROWS = 1, 2, 3, 4
 PT_OPT_TRAV_INNER_RUN, PT_OPT_COUNT_STEPS, PT_OPT_REF_LEAF_BOXES = 7, 8, 9
@@ -52,14 +53,13 @@ class PtError(RuntimeError):
     pass
 
 
-_lib = None
+_libs = {}
 
 
 def load_library(path: str = LIB_PATH) -> C.CDLL:
-    """Load libpt_b200.so; raises (never falls back) when it has not been built."""
-    global _lib
-    if _lib is not None:
-        return _lib
+    """Load libpt_b200.so (or the variant at `path`); raises (never falls back) when it has not been built."""
+    if path in _libs:
+        return _libs[path]
     if not os.path.exists(path):
         raise PtError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                       "(there is no CPU fallback for the render path)")
@@ -93,7 +93,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.pt_texture_destroy.argtypes = [C.c_void_p, C.c_uint64]
     for n in ("pt_build", "pt_synchronize", "pt_reset_accum", "pt_scene_destroy"):
         getattr(lib, n).argtypes = [C.c_void_p]
-    _lib = lib
+    _libs[path] = lib
     return lib
 
 
@@ -156,8 +156,8 @@ def camera_control(cam, op: int, arg: float, move_speed: float = 50.0):
 class Renderer:
     """One scene on the current CUDA device (the reference's `PathTracer` + `SceneBVH`)."""
 
-    def __init__(self, scene=None, sky: np.ndarray | None = None):
-        self.lib = load_library()
+    def __init__(self, scene=None, sky: np.ndarray | None = None, lib_path: str = LIB_PATH):
+        self.lib = load_library(lib_path)
         h = C.c_void_p()
         self._check(self.lib.pt_scene_create(C.byref(h)))
         self.h = h

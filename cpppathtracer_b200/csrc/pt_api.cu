@@ -657,9 +657,7 @@ int display_dispatch(pt_scene* s, const pt_camera* cam, int max_depth, uint64_t 
         CK(cudaMemsetAsync(s->disp_mix.p, 0, npix * sizeof(float4), s->stream));
         s->disp_w = cam->width; s->disp_h = cam->height;
     }
-    const uint32_t saved_wave = s->opt_wave_paths;
     int rc = render_async(s, cam, 1, max_depth, seed, sample_idx - 1, /*accumulate=*/false, s->disp_normal.p);
-    s->opt_wave_paths = saved_wave;
     if (rc) return rc;
     dim3 tb(32, 8), gb((cam->width + 31) / 32, (cam->height + 7) / 8);
     k_denoise_mix<<<gb, tb, 0, s->stream>>>(cam->width, cam->height, s->path_out.p, s->disp_normal.p, s->disp_mix.p,
@@ -676,7 +674,13 @@ extern "C" {
 
 const char* pt_last_error(void) { return g_err.c_str(); }
 int pt_set_error_text(const char* msg) { g_err = msg ? msg : ""; return 0; }   // for the other translation units of the library
-const char* pt_version(void) { return "cpppathtracer_b200 0.1 (sm_100a wavefront)"; }
+const char* pt_version(void) {
+#ifdef PT_VARIANT_FMA
+    return "cpppathtracer_b200 0.1 (sm_100a wavefront, fma-contracted arithmetic)";
+#else
+    return "cpppathtracer_b200 0.1 (sm_100a wavefront)";
+#endif
+}
 
 int pt_scene_create(pt_scene** out) {
     if (!out) return fail(PT_ERR_INVALID, "null out");
