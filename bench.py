@@ -167,6 +167,27 @@ def reference_arm(args, out):
         "gpu_launches": 0})])
 
 
+def fp32_view(r, cam, depth, mrays_per_s, sm_mhz):
+    """SURVEY.md 8(d)'s second ceiling: algorithmic FP32 work per segment from THIS BVH's measured visit counts
+    (instrumented kernel, 2 spp) against 148 SMs x 128 lanes x 2 flop x clock."""
+    from cpppathtracer_b200 import api
+    r.set_option(api.PT_OPT_COUNT_STEPS, 1)
+    r.reset_accum()
+    r.render(cam, 2, depth, seed=7)
+    st = r.stats()
+    r.set_option(api.PT_OPT_COUNT_STEPS, 0)
+    nodes, prims = st["node_steps"] / st["segments"], st["prim_tests"] / st["segments"]
+    # per node visit two child boxes of 18 flops (slab test with precomputed 1/d), ~30 per sphere test, 10 for the
+    # platform, ~150 per shade, 40 per camera ray (SURVEY.md 8d)
+    flops_seg = nodes * 2 * 18 + prims * 30 + 10 + 150 + 40 * st["paths"] / st["segments"]
+    peak = 148 * 128 * 2 * (sm_mhz or 1965.0) * 1e6 / 1e12
+    achieved = mrays_per_s * 1e6 * flops_seg / 1e12
+    return {"bound": "fp32 issue", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "algorithmic_flops_per_segment": flops_seg, "node_visits_per_segment": nodes, "prim_tests_per_segment": prims,
+            "note": "algorithmic flops only (min/max, compares, address and stack arithmetic, Philox and IEEE division "
+                    "sequences are not counted): the kernel issues 2.4-3.2 of 4 warp-instructions per clock per SM"}
+
+
 def fma_variant_leg(sc, sky):
     """Same workload through libpt_b200_fma.so (reported beside the headline, which is the default library's)."""
     from cpppathtracer_b200 import api
@@ -365,6 +386,7 @@ def main():
                     "steps": e2e_steps, "what": "pt_update_prim + pt_build (upload, LBVH) + pt_render_frame + pt_read_accum into pinned host memory"},
             "gpu_launches": int(launches), "clocks": clocks,
         }
+        line["roofline_fp32"] = fp32_view(r, cam, depth, line["path"]["mrays_per_s"], (clocks or {}).get("sm_mhz"))
         if world == 1 and not args.no_baselines:
             line["variants"] = {"libpt_b200_fma.so (nvcc-contracted arithmetic of the reference's CUDA build)": fma_variant_leg(sc, sky)}
             line["cpu_baseline"] = cpu_baseline_leg(sc, sky)
