@@ -60,3 +60,28 @@ def test_facade_driver_end_to_end(tmp_path):
     assert out[2].startswith("after_move idx 1 changed 1")
     assert out[3] == "after_update changed 1"
     assert out[4] == "threaded frames 7"
+
+
+def _compile_c(src, out):
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    subprocess.check_call([cc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-o", str(out), os.path.join(ROOT, "tests", "facade", src),
+                           f"-L{LIBDIR}", "-lpt_b200", f"-Wl,-rpath,{LIBDIR}"])
+
+
+def test_abi_header_is_plain_c(tmp_path):
+    """include/pt_api.h compiles as pedantic C99 and links from C; without a device the example reports it and stops."""
+    import torch
+    exe = tmp_path / "abi_c_example"
+    _compile_c("abi_c_example.c", exe)
+    if torch.cuda.is_available():
+        pytest.skip("device run is test_abi_c_example_runs")
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 3 and r.stdout.startswith("NO_DEVICE")
+
+
+@pytest.mark.gpu
+def test_abi_c_example_runs(tmp_path):
+    exe = tmp_path / "abi_c_example"
+    _compile_c("abi_c_example.c", exe)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("OK samples 4 mean 0."), r.stdout + r.stderr
