@@ -78,13 +78,39 @@ struct LaneRay {
     uint32_t best_code;
     uint32_t slot;
     int node, sp;
+#if PT_STACK_TOP
+    int top;               // top of the stack, in a register: a pop hands it out and starts loading the next entry,
+                           // whose latency then hides behind the node visit instead of stalling the node fetch
+#endif
 };
 #define PT_SENTINEL 0x7fffffff
+#ifndef PT_FILE_ONESHOT
+#define PT_FILE_ONESHOT 1
+#endif
+#ifndef PT_RCP_APPROX
+#define PT_RCP_APPROX 1
+#endif
+#ifndef PT_STACK_TOP
+#define PT_STACK_TOP 1
+#endif
 
 __device__ __forceinline__ float tie_tmax(uint32_t idx, float best_t, uint32_t best_code) {
     // see trace_closest: one ulp above best_t when primitive idx outranks the current holder
     const uint32_t holder = (best_code == PT_MISS_CODE) ? 0u : (best_code >> 3);
     return (idx < holder) ? __uint_as_float(__float_as_uint(best_t) + 1u) : best_t;
+}
+
+// 1/d for the slab tests.  Culling only has to be conservative, so the one-instruction MUFU.RCP (relative error
+// <= 2^-23) replaces the ~8-instruction IEEE division: a slab distance is then off by <= 1.5 ulp of |plane/d| +
+// 2 ulp of |o/d|, inside the 4-ulp inflation of the boxes and the 4-ulp slack of the ray interval.
+__device__ __forceinline__ float cull_rcp(float x) {
+#if PT_RCP_APPROX
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return 1.0f / x;
+#endif
 }
 
 __device__ __forceinline__ void lane_begin(const SceneDev& sc, LaneRay& r, int* stack) {
@@ -95,9 +121,9 @@ __device__ __forceinline__ void lane_begin(const SceneDev& sc, LaneRay& r, int* 
         if (hit_platform(sc.plat_y[k], r.o, r.d, r.tmin, tm)) { r.best_t = tm; r.best_code = (prim << 3) | PART_PLATFORM; }
     }
     // |1/d| is capped at 1e18 so that c*(1/d) and h*|1/d| stay finite (no inf - inf) for coordinates up to 1e20
-    r.ix = 1.0f / (fabsf(r.d.x) > 1e-18f ? r.d.x : copysignf(1e-18f, r.d.x));
-    r.iy = 1.0f / (fabsf(r.d.y) > 1e-18f ? r.d.y : copysignf(1e-18f, r.d.y));
-    r.iz = 1.0f / (fabsf(r.d.z) > 1e-18f ? r.d.z : copysignf(1e-18f, r.d.z));
+    r.ix = cull_rcp(fabsf(r.d.x) > 1e-18f ? r.d.x : copysignf(1e-18f, r.d.x));
+    r.iy = cull_rcp(fabsf(r.d.y) > 1e-18f ? r.d.y : copysignf(1e-18f, r.d.y));
+    r.iz = cull_rcp(fabsf(r.d.z) > 1e-18f ? r.d.z : copysignf(1e-18f, r.d.z));
     r.ox = r.o.x * r.ix; r.oy = r.o.y * r.iy; r.oz = r.o.z * r.iz;
     // |fma(p, 1/d, -o/d) - (p-o)/d| <= ~3 ulp of |o/d| (rounding of 1/d, of o/d and of the fma); culling only has
     // to be conservative, so both interval ends get that much slack (plus the 4-ulp inflation of the leaf boxes)
@@ -106,7 +132,25 @@ __device__ __forceinline__ void lane_begin(const SceneDev& sc, LaneRay& r, int* 
     r.hi = r.best_t * 1.0000005f + r.slack;
     r.sp = 0;
     stack[r.sp++] = PT_SENTINEL;
+#if PT_STACK_TOP
+    r.top = PT_SENTINEL;
+#endif
     r.node = sc.n_tree_prims > 0 ? 0 : PT_SENTINEL;
+}
+
+__device__ __forceinline__ void stack_push(LaneRay& r, int* stack, int x) {
+#if PT_STACK_TOP
+    stack[r.sp++] = r.top; r.top = x;
+#else
+    stack[r.sp++] = x;
+#endif
+}
+__device__ __forceinline__ int stack_pop(LaneRay& r, int* stack) {
+#if PT_STACK_TOP
+    const int x = r.top; r.top = stack[--r.sp]; return x;    // sp >= 1 here: entry 0 is the sentinel written by lane_begin
+#else
+    return stack[--r.sp];
+#endif
 }
 
 // One 64-byte node = two 256-bit loads (LDG.E.256, new on sm_100): half the LSU instructions and L1 wavefronts
@@ -141,12 +185,12 @@ __device__ __forceinline__ void lane_inner(const SceneDev& sc, LaneRay& r, int* 
             const bool a_near = ea <= eb;
             r.node = a_near ? ca : cb;
             const int far = a_near ? cb : ca;
-            stack[r.sp++] = far;
+            stack_push(r, stack, far);
             // the far child is visited later (if at all): start pulling its node towards L1 now
             if (far >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(sc.nodes + 4 * (size_t)far));
         } else if (ha) r.node = ca;
         else if (hb) r.node = cb;
-        else r.node = stack[--r.sp];
+        else r.node = stack_pop(r, stack);
     }
 }
 __device__ __forceinline__ void lane_leaf(const SceneDev& sc, LaneRay& r, int* stack) {
@@ -160,7 +204,7 @@ __device__ __forceinline__ void lane_leaf(const SceneDev& sc, LaneRay& r, int* s
         if ((leaf & 3u) == 2u) h = hit_cylinder(g0, __ldg(&sc.geo1[prim]).x, r.o, r.d, r.tmin, tm, part);
         else h = hit_sphere(g0, r.o, r.d, r.tmin, tm, part);
         if (h) { r.best_t = tm; r.best_code = (prim << 3) | (uint32_t)part; r.hi = tm * 1.0000005f + r.slack; }
-        r.node = stack[--r.sp];
+        r.node = stack_pop(r, stack);
     }
 }
 
@@ -348,6 +392,29 @@ __global__ void PT_BOUNCE_BOUNDS k_bounce(const BounceArgs a) {
             int obin = -1;
             if (alive)
                 obin = (r.best_code == PT_MISS_CODE) ? BIN_MISS : (int)(__float_as_uint(__ldg(&sc.geo1[r.best_code >> 3]).w) >> 28);
+#if PT_FILE_ONESHOT
+            // One atomic INSTRUCTION per chunk: lane b reserves the slots of bin b (up to NUM_BINS lanes issue
+            // together, one round trip to L2 instead of one per non-empty bin), then every lane writes its record
+            // once.  (v6 looped over the bins: the warp waited for up to five dependent atomics per chunk, 6 % of
+            // the stall samples of a bounce launch, and ran each bin's stores with that bin's lanes only.)
+            uint32_t my_mask = 0u, lane_mask = 0u;
+#pragma unroll
+            for (int b = 0; b < NUM_BINS; ++b) {
+                const uint32_t m = __ballot_sync(PT_FULL, obin == b);
+                if (obin == b) my_mask = m;
+                if ((int)lane == b) lane_mask = m;
+            }
+            uint32_t base = 0u;
+            if (lane_mask) base = atomicAdd(&a.ctrl_out->bin_count[lane & 7u].v, (uint32_t)__popc(lane_mask));
+            base = __shfl_sync(PT_FULL, base, obin & 7);
+            if (obin >= 0) {
+                const size_t j = (size_t)obin * a.hq_out.capacity + base + __popc(my_mask & ((1u << lane) - 1u));
+                __stcs(&a.hq_out.o[j], make_float4(r.o.x, r.o.y, r.o.z, __uint_as_float(pixel)));
+                __stcs(&a.hq_out.d[j], make_float4(r.d.x, r.d.y, r.d.z, __uint_as_float(s)));
+                __stcs(&a.hq_out.thr[j], make_float4(thr.x, thr.y, thr.z, 0.f));
+                __stcs(&a.hq_out.hit[j], make_uint2(__float_as_uint(r.best_t), r.best_code));
+            }
+#else
 #pragma unroll
             for (int b = 0; b < NUM_BINS; ++b) {
                 const uint32_t m = __ballot_sync(PT_FULL, obin == b);
@@ -365,6 +432,7 @@ __global__ void PT_BOUNCE_BOUNDS k_bounce(const BounceArgs a) {
                     }
                 }
             }
+#endif
         }
     }
     // statistics: rays traced by this launch (one atomic per warp), optional visit counters
