@@ -464,6 +464,7 @@ int render_async(pt_scene* s, const pt_camera* cam, int spp, int max_depth, uint
     BounceArgs args;
     memset(&args, 0, sizeof(args));
     args.sc = scene_dev(s); args.key = key; args.npix = npix; args.max_depth = max_depth; args.inner_run = s->opt_inner_run;
+    args.cam_tiled = (cam->width % 8 == 0 && cam->height % 4 == 0) ? 1 : 0;
     args.cam = frame; args.path_out = s->path_out.p; args.gbuf_normal = gbuf_normal; args.step_counters = s->seg_counter.p + 1;
     const bool timing = s->opt_stage_timing != 0;
     size_t ev_i = 0;

@@ -20,6 +20,19 @@ namespace pt {
 #define PT_MISS_CODE 0xFFFFFFFFu
 #define PT_STACK 64
 #define PT_FULL 0xffffffffu
+// build-time switches of k_bounce (tools/build_variants.sh times the alternatives on one box)
+#ifndef PT_FILE_ONESHOT
+#define PT_FILE_ONESHOT 1
+#endif
+#ifndef PT_RCP_APPROX
+#define PT_RCP_APPROX 1
+#endif
+#ifndef PT_CAMERA_TILES
+#define PT_CAMERA_TILES 1
+#endif
+#ifndef PT_STACK_TOP
+#define PT_STACK_TOP 1
+#endif
 
 // One control block per bounce, zeroed once per wave.  Every counter that takes atomics sits on its own
 // 128-byte line (its own L2 slice queue): v1 kept them in one 64-byte line and k_shade spent its time
@@ -84,15 +97,6 @@ struct LaneRay {
 #endif
 };
 #define PT_SENTINEL 0x7fffffff
-#ifndef PT_FILE_ONESHOT
-#define PT_FILE_ONESHOT 1
-#endif
-#ifndef PT_RCP_APPROX
-#define PT_RCP_APPROX 1
-#endif
-#ifndef PT_STACK_TOP
-#define PT_STACK_TOP 1
-#endif
 
 __device__ __forceinline__ float tie_tmax(uint32_t idx, float best_t, uint32_t best_code) {
     // see trace_closest: one ulp above best_t when primitive idx outranks the current holder
@@ -193,19 +197,20 @@ __device__ __forceinline__ void lane_inner(const SceneDev& sc, LaneRay& r, int* 
         else r.node = stack_pop(r, stack);
     }
 }
+__device__ __forceinline__ void lane_leaf_test(const SceneDev& sc, LaneRay& r, int code) {
+    const uint32_t leaf = (uint32_t)~code;
+    const uint32_t prim = leaf >> 2;
+    const float4 g0 = __ldg(&sc.geo0[prim]);
+    int part = 0;
+    float tm = tie_tmax(prim, r.best_t, r.best_code);
+    bool h;
+    if ((leaf & 3u) == 2u) h = hit_cylinder(g0, __ldg(&sc.geo1[prim]).x, r.o, r.d, r.tmin, tm, part);
+    else h = hit_sphere(g0, r.o, r.d, r.tmin, tm, part);
+    if (h) { r.best_t = tm; r.best_code = (prim << 3) | (uint32_t)part; r.hi = tm * 1.0000005f + r.slack; }
+}
 __device__ __forceinline__ void lane_leaf(const SceneDev& sc, LaneRay& r, int* stack) {
-    {
-        const uint32_t leaf = (uint32_t)~r.node;
-        const uint32_t prim = leaf >> 2;
-        const float4 g0 = __ldg(&sc.geo0[prim]);
-        int part = 0;
-        float tm = tie_tmax(prim, r.best_t, r.best_code);
-        bool h;
-        if ((leaf & 3u) == 2u) h = hit_cylinder(g0, __ldg(&sc.geo1[prim]).x, r.o, r.d, r.tmin, tm, part);
-        else h = hit_sphere(g0, r.o, r.d, r.tmin, tm, part);
-        if (h) { r.best_t = tm; r.best_code = (prim << 3) | (uint32_t)part; r.hi = tm * 1.0000005f + r.slack; }
-        r.node = stack_pop(r, stack);
-    }
+    lane_leaf_test(sc, r, r.node);
+    r.node = stack_pop(r, stack);
 }
 
 // ---- the bounce kernel ---------------------------------------------------------------------------------------
@@ -233,6 +238,7 @@ struct BounceArgs {
     int segment;              // index k of the segment traced by this launch (shaded hits belong to k-1)
     int max_depth;
     int trace;                // 0: shade only (the launch after the last segment)
+    int cam_tiled;            // SRC_CAMERA: width % 8 == 0 and height % 4 == 0, chunks are 8x4 pixel tiles
     int inner_run;            // inner nodes a lane may walk before the warp regroups for primitive tests
     CameraFrame cam;          // SRC_CAMERA
     uint32_t n_paths;
@@ -346,11 +352,20 @@ __global__ void PT_BOUNCE_BOUNDS k_bounce(const BounceArgs a) {
                 if (pid < a.n_paths) {
                     s = pid / a.npix;
                     pixel = pid - s * a.npix;
+#if PT_CAMERA_TILES
+                    // a chunk covers an 8x4 pixel tile instead of 32 pixels of one row: the 32 primary rays of a warp
+                    // then share more of their walk (fewer distinct nodes per fetch, closer walk lengths)
+                    if (a.cam_tiled) {
+                        const uint32_t tile = pixel >> 5, in_tile = pixel & 31u, tiles_x = (uint32_t)a.cam.width >> 3;
+                        const uint32_t ty = tile / tiles_x, tx = tile - ty * tiles_x;
+                        pixel = (ty * 4u + (in_tile >> 3)) * (uint32_t)a.cam.width + tx * 8u + (in_tile & 7u);
+                    }
+#endif
                     const int y = pixel / (uint32_t)a.cam.width;
                     const int x = pixel - y * (uint32_t)a.cam.width;
                     const float4 U = philox_uniform4(a.key, pixel, a.first_sample + s, 0u);
                     camera_ray(a.cam, x, y, U, r.o, r.d);
-                    if (sc.has_emitters) a.path_out[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (sc.has_emitters) a.path_out[(size_t)s * a.npix + pixel] = make_float4(0.f, 0.f, 0.f, 0.f);
                     alive = true;
                 }
             } else if (SRC == SRC_RAYS) {
