@@ -30,9 +30,10 @@ METRIC = "Mpaths/s at 1080p, max depth 8"
 WORKLOAD = {"workload": "C2: floor + 1000 mixed-material spheres, 1920x1080, 64 spp, depth 8",
             "width": 1920, "height": 1080, "spp": 64, "max_depth": 8, "n_spheres": 1000, "scene_seed": 12345,
             "l2": "hit queues (3.7 GB streamed per 16-spp wave) exceed the 126 MB L2; no explicit flush"}
-# Algorithmic HBM bytes of the dominant kernel k_bounce: every path segment costs one
+# Algorithmic HBM bytes of the dominant kernel k_bounce: every path segment THAT HITS costs one
 # 56-byte hit record written by the launch that traces it and read by the launch that shades it (rays never leave
-# registers), every path one 16-byte radiance write.  SURVEY.md 8(d) budgets 144 B/segment + 16 B/path for a
+# registers; a segment that leaves the scene is shaded by the sky where it ends), every path one 16-byte radiance
+# write.  SURVEY.md 8(d) budgets 144 B/segment + 16 B/path for a
 # wavefront design that also keeps rays in HBM; that figure is reported beside this one.
 ALG_BYTES_PER_SEGMENT = 112
 ALG_BYTES_PER_PATH = 16
@@ -355,7 +356,8 @@ def main():
         segs = st["segments"]                      # rays traced in the last frame on this rank
         kern_ms = st["traverse_ms"] + st["shade_ms"]   # all k_bounce launches of the last frame (CUDA events per launch)
         n_launch = max(st["waves"] * (depth + 1), 1)
-        alg_bytes = ALG_BYTES_PER_SEGMENT * segs + ALG_BYTES_PER_PATH * st["paths"]
+        hits = st["hit_records"]                   # segments that hit something: the only ones with a queue record
+        alg_bytes = ALG_BYTES_PER_SEGMENT * hits + ALG_BYTES_PER_PATH * st["paths"]
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else None
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traverse_traffic.json")
@@ -374,9 +376,10 @@ def main():
                          "algorithmic_bytes_per_launch": alg_bytes / n_launch, "avg_launch_ms": kern_ms / n_launch,
                          "launches_per_step": n_launch,
                          "share_of_step": kern_ms / st["render_ms"] if st["render_ms"] > 0 else None,
-                         "note": "bound by instruction issue x SIMD efficiency (IPC 2.4-3.2 of 4, 17-27 of 32 lanes active, "
-                                 "long-scoreboard on L1/L2 node fetches; profiles/r01_v6_summary.md), not by HBM; DRAM traffic "
-                                 "equals the algorithmic bytes (ratio 1.02)"},
+                         "hit_records_per_step": hits,
+                         "note": "bound by instruction issue x SIMD efficiency (IPC 2.5-3.2 of 4, 17-30 of 32 lanes active, "
+                                 "long-scoreboard on L1/L2 node fetches; profiles/r01_v8_summary.md), not by HBM; DRAM traffic "
+                                 "equals the algorithmic bytes"},
             "path": {"mrays_per_s": segs / (st["render_ms"] * 1e-3) / 1e6 if st["render_ms"] > 0 else None,
                      "segments_per_path": segs / st["paths"], "render_ms_last_frame": st["render_ms"],
                      "bounce_kernel_ms": kern_ms,

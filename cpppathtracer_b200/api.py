@@ -35,7 +35,7 @@ class PtStats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("segments", C.c_uint64), ("launches", C.c_uint64), ("render_ms", C.c_float),
                 ("traverse_ms", C.c_float), ("shade_ms", C.c_float), ("build_ms", C.c_float),
                 ("bvh_nodes", C.c_uint32), ("wave_paths", C.c_uint32), ("traverse_launches", C.c_uint32),
-                ("waves", C.c_uint32), ("node_steps", C.c_uint64), ("prim_tests", C.c_uint64)]
+                ("waves", C.c_uint32), ("node_steps", C.c_uint64), ("prim_tests", C.c_uint64), ("hit_records", C.c_uint64)]
 
 
 EXPORTS = [

@@ -521,7 +521,7 @@ int finish_frame(pt_scene* s, int max_depth_hint) {
     CK(cudaMemcpyAsync(seg4, s->seg_counter.p, sizeof(seg4), cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     CK(cudaEventElapsedTime(&s->stats.render_ms, s->ev0, s->ev1));
-    s->stats.segments = seg4[0]; s->stats.node_steps = seg4[1]; s->stats.prim_tests = seg4[2];
+    s->stats.segments = seg4[0]; s->stats.node_steps = seg4[1]; s->stats.prim_tests = seg4[2]; s->stats.hit_records = seg4[3];
     if (s->opt_stage_timing && s->stage_events.size() >= 2) {
         // per wave: one event before each of the max_depth+1 k_bounce launches and one after the last.
         // traverse_ms = launches that trace (segments 0 .. max_depth-1; they also shade the previous segment's hits),

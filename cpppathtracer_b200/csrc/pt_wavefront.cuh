@@ -30,6 +30,9 @@ namespace pt {
 #ifndef PT_CAMERA_TILES
 #define PT_CAMERA_TILES 1
 #endif
+#ifndef PT_MISS_INLINE
+#define PT_MISS_INLINE 1
+#endif
 #ifndef PT_STACK_TOP
 #define PT_STACK_TOP 1
 #endif
@@ -256,6 +259,15 @@ struct BounceArgs {
     uint32_t* ray_steps;                 // COUNT_STEPS + SRC_RAYS: visits per ray (diagnostics)
 };
 
+// Miss, path_tracer.cu:117-122: the path ends with the sky seen through its throughput
+__device__ __forceinline__ void shade_miss(const BounceArgs& a, float3 d, float3 thr, size_t pid, bool first_segment) {
+    const float3 c = thr * sky_radiance(a.sc.sky, d);
+    if (a.sc.has_emitters) { float4 p = a.path_out[pid]; a.path_out[pid] = make_float4(p.x + c.x, p.y + c.y, p.z + c.z, 0.f); }
+    else a.path_out[pid] = make_float4(c.x, c.y, c.z, 0.f);
+    // G-buffer of the display pipeline: a first-segment miss records -dir (path_tracer.cu:152)
+    if (a.gbuf_normal != nullptr && first_segment) a.gbuf_normal[pid] = make_float4(-d.x, -d.y, -d.z, 0.f);
+}
+
 // Shade (or miss) item `item` of shader bin `bin` of the input hit queue.  Returns true and the next ray when the
 // path goes on; paths that end write their radiance.
 __device__ __forceinline__ bool shade_hit_item(const BounceArgs& a, int bin, uint32_t item, bool last_shade, float3& ray_o,
@@ -272,15 +284,7 @@ __device__ __forceinline__ bool shade_hit_item(const BounceArgs& a, int bin, uin
     const size_t pid = (size_t)s * a.npix + pixel;
     const float3 o = f3(o4.x, o4.y, o4.z), d = f3(d4.x, d4.y, d4.z);
     thr = f3(t4.x, t4.y, t4.z);
-    if (bin == BIN_MISS) {
-        // Miss, path_tracer.cu:117-122: the path ends with the sky seen through its throughput
-        const float3 c = thr * sky_radiance(sc.sky, d);
-        if (sc.has_emitters) { float4 p = a.path_out[pid]; a.path_out[pid] = make_float4(p.x + c.x, p.y + c.y, p.z + c.z, 0.f); }
-        else a.path_out[pid] = make_float4(c.x, c.y, c.z, 0.f);
-        // G-buffer of the display pipeline: a first-segment miss records -dir (path_tracer.cu:152)
-        if (a.gbuf_normal != nullptr && a.segment == 1) a.gbuf_normal[pid] = make_float4(-d.x, -d.y, -d.z, 0.f);
-        return false;
-    }
+    if (bin == BIN_MISS) { shade_miss(a, d, thr, pid, a.segment == 1); return false; }
     const uint32_t prim = h.y >> 3;
     const float4 g0 = __ldg(&sc.geo0[prim]);
     const uint32_t mslot = __float_as_uint(__ldg(&sc.geo1[prim]).w) & 0x0fffffffu;
@@ -407,6 +411,11 @@ __global__ void PT_BOUNCE_BOUNDS k_bounce(const BounceArgs a) {
             int obin = -1;
             if (alive)
                 obin = (r.best_code == PT_MISS_CODE) ? BIN_MISS : (int)(__float_as_uint(__ldg(&sc.geo1[r.best_code >> 3]).w) >> 28);
+#if PT_MISS_INLINE
+            // rays that leave the scene end here: the sky is looked up by the lanes that missed instead of sending a
+            // 56-byte record through the miss bin to the next launch
+            if (obin == BIN_MISS) { shade_miss(a, r.d, thr, (size_t)s * a.npix + pixel, a.segment == 0); obin = -1; }
+#endif
 #if PT_FILE_ONESHOT
             // One atomic INSTRUCTION per chunk: lane b reserves the slots of bin b (up to NUM_BINS lanes issue
             // together, one round trip to L2 instead of one per non-empty bin), then every lane writes its record
@@ -482,10 +491,15 @@ __global__ void __launch_bounds__(256) k_accumulate(uint32_t npix, uint32_t n_sa
 
 // per-wave bookkeeping: rays traced = sum of the bounce input queues (diagnostic counter, 1 thread)
 __global__ void k_wave_stats(int max_depth, const BounceCtrl* __restrict__ ctrl, unsigned long long* __restrict__ segments) {
-    // segments[0] rays traced, [1] inner-node steps, [2] primitive tests (the latter two only with PT_OPT_COUNT_STEPS)
-    unsigned long long n = 0;
-    for (int b = 0; b < max_depth; ++b) n += ctrl[b].rays.v;   // ctrl[k].rays = rays traced as segment k
-    *segments += n;
+    // segments[0] rays traced, [1] inner-node steps, [2] primitive tests (the latter two only with PT_OPT_COUNT_STEPS),
+    // [3] hit records that went through the hit queues (one per segment that hit something; misses end in place)
+    unsigned long long n = 0, h = 0;
+    for (int b = 0; b < max_depth; ++b) {
+        n += ctrl[b].rays.v;   // ctrl[k].rays = rays traced as segment k
+        for (int q = 0; q < NUM_BINS; ++q) h += ctrl[b].bin_count[q].v;
+    }
+    segments[0] += n;
+    segments[3] += h;
 }
 
 }  // namespace pt

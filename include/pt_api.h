@@ -73,6 +73,7 @@ typedef struct pt_stats {
     uint32_t waves;           /* waves of the last pt_render_frame                            */
     uint64_t node_steps;      /* inner BVH nodes visited (only with PT_OPT_COUNT_STEPS)       */
     uint64_t prim_tests;      /* sphere / cylinder tests run (only with PT_OPT_COUNT_STEPS)   */
+    uint64_t hit_records;     /* 56-byte hit records that went through the hit queues (segments that hit) */
 } pt_stats;
 
 enum {
