@@ -21,9 +21,6 @@ namespace pt {
 #define PT_STACK 64
 #define PT_FULL 0xffffffffu
 // build-time switches of k_bounce (tools/build_variants.sh times the alternatives on one box)
-#ifndef PT_FILE_ONESHOT
-#define PT_FILE_ONESHOT 1
-#endif
 #ifndef PT_RCP_APPROX
 #define PT_RCP_APPROX 1
 #endif
@@ -120,13 +117,17 @@ __device__ __forceinline__ float cull_rcp(float x) {
 #endif
 }
 
-__device__ __forceinline__ void lane_begin(const SceneDev& sc, LaneRay& r, int* stack) {
-    r.best_code = PT_MISS_CODE;
+// platforms are kept out of the tree: tested first, they also give the walk its first tmax
+__device__ __forceinline__ void lane_platforms(const SceneDev& sc, float3 o, float3 d, float tmin, float& best_t, uint32_t& best_code) {
+    best_code = PT_MISS_CODE;
     for (int k = 0; k < sc.n_plat; ++k) {
         const uint32_t prim = (uint32_t)sc.plat_id[k];
-        float tm = tie_tmax(prim, r.best_t, r.best_code);
-        if (hit_platform(sc.plat_y[k], r.o, r.d, r.tmin, tm)) { r.best_t = tm; r.best_code = (prim << 3) | PART_PLATFORM; }
+        float tm = tie_tmax(prim, best_t, best_code);
+        if (hit_platform(sc.plat_y[k], o, d, tmin, tm)) { best_t = tm; best_code = (prim << 3) | PART_PLATFORM; }
     }
+}
+// walk state of a ray whose origin, direction, tmin and (best_t, best_code) are set
+__device__ __forceinline__ void lane_setup(const SceneDev& sc, LaneRay& r, int* stack) {
     // |1/d| is capped at 1e18 so that c*(1/d) and h*|1/d| stay finite (no inf - inf) for coordinates up to 1e20
     r.ix = cull_rcp(fabsf(r.d.x) > 1e-18f ? r.d.x : copysignf(1e-18f, r.d.x));
     r.iy = cull_rcp(fabsf(r.d.y) > 1e-18f ? r.d.y : copysignf(1e-18f, r.d.y));
@@ -143,6 +144,10 @@ __device__ __forceinline__ void lane_begin(const SceneDev& sc, LaneRay& r, int* 
     r.top = PT_SENTINEL;
 #endif
     r.node = sc.n_tree_prims > 0 ? 0 : PT_SENTINEL;
+}
+__device__ __forceinline__ void lane_begin(const SceneDev& sc, LaneRay& r, int* stack) {
+    lane_platforms(sc, r.o, r.d, r.tmin, r.best_t, r.best_code);
+    lane_setup(sc, r, stack);
 }
 
 __device__ __forceinline__ void stack_push(LaneRay& r, int* stack, int x) {
@@ -309,6 +314,42 @@ __device__ __forceinline__ bool shade_hit_item(const BounceArgs& a, int bin, uin
     return alive;
 }
 
+// Files the result of a traced segment: a ray that left the scene is shaded by the sky in place (its path ends), a
+// hit goes to the hit queue of its shader bin.  Called by all 32 lanes.
+__device__ __forceinline__ void file_hit(const BounceArgs& a, uint32_t lane, bool alive, float3 o, float3 d, float3 thr,
+                                         uint32_t pixel, uint32_t s, float best_t, uint32_t best_code) {
+    const SceneDev& sc = a.sc;
+    int obin = -1;
+    if (alive)
+        obin = (best_code == PT_MISS_CODE) ? BIN_MISS : (int)(__float_as_uint(__ldg(&sc.geo1[best_code >> 3]).w) >> 28);
+#if PT_MISS_INLINE
+    // rays that leave the scene end here: the sky is looked up by the lanes that missed instead of sending a
+    // 56-byte record through a miss bin to the next launch (v7 did: +9 % on C2 without it)
+    if (obin == BIN_MISS) { shade_miss(a, d, thr, (size_t)s * a.npix + pixel, a.segment == 0); obin = -1; }
+#endif
+    // One atomic INSTRUCTION per chunk: lane b reserves the slots of bin b (up to NUM_BINS lanes issue together, one
+    // round trip to L2 instead of one per non-empty bin), then every lane writes its record once.  (v6 looped over
+    // the bins: the warp waited for up to five dependent atomics per chunk, 6 % of the stall samples of a bounce
+    // launch, and ran each bin's stores with that bin's lanes only.)
+    uint32_t my_mask = 0u, lane_mask = 0u;
+#pragma unroll
+    for (int b = 0; b < NUM_BINS; ++b) {
+        const uint32_t m = __ballot_sync(PT_FULL, obin == b);
+        if (obin == b) my_mask = m;
+        if ((int)lane == b) lane_mask = m;
+    }
+    uint32_t base = 0u;
+    if (lane_mask) base = atomicAdd(&a.ctrl_out->bin_count[lane & 7u].v, (uint32_t)__popc(lane_mask));
+    base = __shfl_sync(PT_FULL, base, obin & 7);
+    if (obin >= 0) {
+        const size_t j = (size_t)obin * a.hq_out.capacity + base + __popc(my_mask & ((1u << lane) - 1u));
+        __stcs(&a.hq_out.o[j], make_float4(o.x, o.y, o.z, __uint_as_float(pixel)));
+        __stcs(&a.hq_out.d[j], make_float4(d.x, d.y, d.z, __uint_as_float(s)));
+        __stcs(&a.hq_out.thr[j], make_float4(thr.x, thr.y, thr.z, 0.f));
+        __stcs(&a.hq_out.hit[j], make_uint2(__float_as_uint(best_t), best_code));
+    }
+}
+
 #if PT_BOUNCE_MIN_BLOCKS > 0
 #define PT_BOUNCE_BOUNDS __launch_bounds__(32 * PT_BOUNCE_WARPS, PT_BOUNCE_MIN_BLOCKS)
 #else
@@ -408,55 +449,7 @@ __global__ void PT_BOUNCE_BOUNDS k_bounce(const BounceArgs a) {
                 if (COUNT_STEPS && alive && a.ray_steps != nullptr) a.ray_steps[slot] = lane_steps;
                 continue;
             }
-            int obin = -1;
-            if (alive)
-                obin = (r.best_code == PT_MISS_CODE) ? BIN_MISS : (int)(__float_as_uint(__ldg(&sc.geo1[r.best_code >> 3]).w) >> 28);
-#if PT_MISS_INLINE
-            // rays that leave the scene end here: the sky is looked up by the lanes that missed instead of sending a
-            // 56-byte record through the miss bin to the next launch
-            if (obin == BIN_MISS) { shade_miss(a, r.d, thr, (size_t)s * a.npix + pixel, a.segment == 0); obin = -1; }
-#endif
-#if PT_FILE_ONESHOT
-            // One atomic INSTRUCTION per chunk: lane b reserves the slots of bin b (up to NUM_BINS lanes issue
-            // together, one round trip to L2 instead of one per non-empty bin), then every lane writes its record
-            // once.  (v6 looped over the bins: the warp waited for up to five dependent atomics per chunk, 6 % of
-            // the stall samples of a bounce launch, and ran each bin's stores with that bin's lanes only.)
-            uint32_t my_mask = 0u, lane_mask = 0u;
-#pragma unroll
-            for (int b = 0; b < NUM_BINS; ++b) {
-                const uint32_t m = __ballot_sync(PT_FULL, obin == b);
-                if (obin == b) my_mask = m;
-                if ((int)lane == b) lane_mask = m;
-            }
-            uint32_t base = 0u;
-            if (lane_mask) base = atomicAdd(&a.ctrl_out->bin_count[lane & 7u].v, (uint32_t)__popc(lane_mask));
-            base = __shfl_sync(PT_FULL, base, obin & 7);
-            if (obin >= 0) {
-                const size_t j = (size_t)obin * a.hq_out.capacity + base + __popc(my_mask & ((1u << lane) - 1u));
-                __stcs(&a.hq_out.o[j], make_float4(r.o.x, r.o.y, r.o.z, __uint_as_float(pixel)));
-                __stcs(&a.hq_out.d[j], make_float4(r.d.x, r.d.y, r.d.z, __uint_as_float(s)));
-                __stcs(&a.hq_out.thr[j], make_float4(thr.x, thr.y, thr.z, 0.f));
-                __stcs(&a.hq_out.hit[j], make_uint2(__float_as_uint(r.best_t), r.best_code));
-            }
-#else
-#pragma unroll
-            for (int b = 0; b < NUM_BINS; ++b) {
-                const uint32_t m = __ballot_sync(PT_FULL, obin == b);
-                if (m) {
-                    uint32_t off = 0;
-                    const int leader = __ffs(m) - 1;
-                    if ((int)lane == leader) off = atomicAdd(&a.ctrl_out->bin_count[b].v, (uint32_t)__popc(m));
-                    off = __shfl_sync(PT_FULL, off, leader);
-                    if (obin == b) {
-                        const size_t j = (size_t)b * a.hq_out.capacity + off + __popc(m & ((1u << lane) - 1u));
-                        __stcs(&a.hq_out.o[j], make_float4(r.o.x, r.o.y, r.o.z, __uint_as_float(pixel)));
-                        __stcs(&a.hq_out.d[j], make_float4(r.d.x, r.d.y, r.d.z, __uint_as_float(s)));
-                        __stcs(&a.hq_out.thr[j], make_float4(thr.x, thr.y, thr.z, 0.f));
-                        __stcs(&a.hq_out.hit[j], make_uint2(__float_as_uint(r.best_t), r.best_code));
-                    }
-                }
-            }
-#endif
+            file_hit(a, lane, alive, r.o, r.d, thr, pixel, s, r.best_t, r.best_code);
         }
     }
     // statistics: rays traced by this launch (one atomic per warp), optional visit counters
