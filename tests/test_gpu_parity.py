@@ -273,12 +273,14 @@ def test_level3_image_vs_oracle(maker, spp, oracle, sky):
     assert 0.90 * ost["segments"] <= st["segments"] <= 1.002 * ost["segments"]
 
 
-def test_level3_depth1_image_is_tight(oracle, sky):
-    """One segment per path: no chaotic amplification, only the texture unit's filter differs."""
-    sc = scenes.demo_scene(320, 180)
+@pytest.mark.parametrize("w,h", [(320, 180), (322, 181), (37, 23)])
+def test_level3_depth1_image_is_tight(w, h, oracle, sky):
+    """One segment per path: no chaotic amplification, only the texture unit's filter differs.  320x180 takes the
+    8x4-tile order of the camera chunks, 322x181 the row order (width not a multiple of 8), 37x23 a ragged last chunk."""
+    sc = scenes.demo_scene(w, h)
     img, ref, st, ost = _render_pair(sc, sky, oracle, 4, seed=3, depth=1)
     assert np.abs(img[..., :3] - ref).max() < 2.5e-3
-    assert st["segments"] == ost["segments"] == 320 * 180 * 4
+    assert st["segments"] == ost["segments"] == w * h * 4
 
 
 def test_properties_at_baseline_size(sky):
