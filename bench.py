@@ -29,7 +29,7 @@ import numpy as np  # noqa: E402
 METRIC = "Mpaths/s at 1080p, max depth 8"
 WORKLOAD = {"workload": "C2: floor + 1000 mixed-material spheres, 1920x1080, 64 spp, depth 8",
             "width": 1920, "height": 1080, "spp": 64, "max_depth": 8, "n_spheres": 1000, "scene_seed": 12345,
-            "l2": "hit queues (3.7 GB streamed per 16-spp wave) exceed the 126 MB L2; no explicit flush"}
+            "l2": "hit queues (about 30 GB streamed per 64-spp frame, written by one launch and read by the next) exceed the 126 MB L2; no explicit flush"}
 # Algorithmic HBM bytes of the dominant kernel k_bounce: every path segment THAT HITS costs one
 # 56-byte hit record written by the launch that traces it and read by the launch that shades it (rays never leave
 # registers; a segment that leaves the scene is shaded by the sky where it ends), every path one 16-byte radiance
@@ -355,7 +355,10 @@ def main():
         peak, peak_src = measured_peaks()
         segs = st["segments"]                      # rays traced in the last frame on this rank
         kern_ms = st["traverse_ms"] + st["shade_ms"]   # all k_bounce launches of the last frame (CUDA events per launch)
-        n_launch = max(st["waves"] * (depth + 1), 1)
+        # k_bounce launches of the last frame: per wave `depth` launches that trace + one that only shades, which is
+        # not enqueued in a scene without emitters (every launch of the timed region minus the two bookkeeping kernels
+        # per wave, per step)
+        n_launch = max(int(round(launches / max(args.steps, 1))) - 2 * st["waves"], 1)
         hits = st["hit_records"]                   # segments that hit something: the only ones with a queue record
         alg_bytes = ALG_BYTES_PER_SEGMENT * hits + ALG_BYTES_PER_PATH * st["paths"]
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else None

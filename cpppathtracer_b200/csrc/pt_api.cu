@@ -71,7 +71,8 @@ struct pt_scene {
     std::map<MatKey, int> material_slots;
     bool dirty = true, built = false;
     // options
-    uint32_t opt_wave_paths = 32u << 20;   // 16 spp per wave at 1080p: 19 GB of hit queues, +3 % over 16 Mi (profiles/r01_v5_summary.md)
+    uint32_t opt_wave_paths = 128u << 20;  // 64 spp per wave at 1080p: 59 GB of hit queues; 5.57 vs 5.40 Gpaths/s with 32 Mi (16 spp), 5.23 with 16 Mi
+                                           // (gpurun_out/wave_sweep_v9.log); ensure_queues halves the wave until the queues fit in free memory
     int opt_stage_timing = 0;
     int opt_tie_order = 1;
     int opt_sky_quarter = 1;
@@ -485,18 +486,25 @@ int render_async(pt_scene* s, const pt_camera* cam, int spp, int max_depth, uint
         args.first_sample = first_sample + s0; args.n_paths = n_paths;
         // segment 0: camera rays -> hit queue 0
         CK(stage_event());
+        // without emitters the hits of the last allowed segment end their paths black: the launch that traces that
+        // segment writes the zeros itself and the shade-only launch is skipped (the display pipeline's G-buffer wants
+        // the first-segment normals, so a depth-1 dispatch keeps it)
+        const bool drop_last = !s->has_emitters && !(gbuf_normal != nullptr && max_depth == 1);
         args.segment = 0; args.trace = 1; args.ctrl_in = ctrl_cam; args.ctrl_out = ctrl + 0; args.hq_out = hit_queues(s, 0);
+        args.drop_last_hits = (drop_last && max_depth == 1) ? 1 : 0;
         launch_bounce<SRC_CAMERA>(s, args, st);
         // segment k: shade the hits of segment k-1, trace the survivors; k == max_depth only shades
         for (int k = 1; k <= max_depth; ++k) {
             CK(stage_event());
+            if (k == max_depth && drop_last) continue;
+            args.drop_last_hits = (drop_last && k == max_depth - 1) ? 1 : 0;
             args.segment = k; args.trace = k < max_depth ? 1 : 0;
             args.ctrl_in = ctrl + (k - 1); args.ctrl_out = ctrl + k;
             args.hq_in = hit_queues(s, (k - 1) & 1); args.hq_out = hit_queues(s, k & 1);
             launch_bounce<SRC_HITS>(s, args, st);
         }
         CK(stage_event());
-        launches += (uint64_t)max_depth + 1;
+        launches += (uint64_t)max_depth + (drop_last ? 0 : 1);
         const int ac_grid = (int)std::min<uint32_t>((npix + 255u) / 256u, (uint32_t)s->sm_count * 8u);
         if (accumulate) k_accumulate<<<ac_grid, 256, 0, st>>>(npix, ns, s->path_out.p, s->accum.p);
         k_wave_stats<<<1, 1, 0, st>>>(max_depth, s->ctrl.p, s->seg_counter.p);

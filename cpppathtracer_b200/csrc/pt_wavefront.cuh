@@ -3,9 +3,9 @@
 // The reference traces one full path per thread in a megakernel (SamplePixel, cuSrc/path_tracer.cu:124-175): a
 // warp runs until its longest path ends, every warp executes every material branch, and the RNG state round-trips
 // through global memory on every draw.  Here a wave of paths advances one segment per launch of k_bounce:
-//     launch 0      : camera rays                          -> closest hit -> hit queue 0, binned by shader
-//     launch k      : shade / miss the hits of segment k-1 -> survivors traced as segment k -> hit queue k
-//     launch depth  : shade / miss only
+//     launch 0      : camera rays                          -> closest hit -> sky (path ends) | hit queue 0, binned by shader
+//     launch k      : shade the hits of segment k-1        -> survivors traced as segment k -> sky | hit queue k
+//     launch depth  : shade only (not enqueued in a scene without emitters: those hits end black)
 //     k_accumulate  : wave radiance into the frame's SUM buffer, in sample order
 // Paths therefore leave the wave the moment they end (no idle lanes waiting for long paths), a warp shades with
 // ONE shader, and a ray lives in registers from the shader that creates it to the hit record it produces.
@@ -27,8 +27,8 @@ namespace pt {
 #ifndef PT_CAMERA_TILES
 #define PT_CAMERA_TILES 1
 #endif
-#ifndef PT_MISS_INLINE
-#define PT_MISS_INLINE 1
+#ifndef PT_PREFETCH_FAR
+#define PT_PREFETCH_FAR 1
 #endif
 #ifndef PT_STACK_TOP
 #define PT_STACK_TOP 1
@@ -198,8 +198,10 @@ __device__ __forceinline__ void lane_inner(const SceneDev& sc, LaneRay& r, int* 
             r.node = a_near ? ca : cb;
             const int far = a_near ? cb : ca;
             stack_push(r, stack, far);
+#if PT_PREFETCH_FAR
             // the far child is visited later (if at all): start pulling its node towards L1 now
             if (far >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(sc.nodes + 4 * (size_t)far));
+#endif
         } else if (ha) r.node = ca;
         else if (hb) r.node = cb;
         else r.node = stack_pop(r, stack);
@@ -225,7 +227,7 @@ __device__ __forceinline__ void lane_leaf(const SceneDev& sc, LaneRay& r, int* s
 // One launch per path segment k.  A warp takes a 32-item chunk of its source, turns it into rays IN REGISTERS,
 // walks them to completion and files the results, binned by shader, into the hit queue of segment k:
 //   SRC_CAMERA : path ids        -> MotionalCamera::RayGen                      -> trace segment 0
-//   SRC_HITS   : hit queue k-1   -> shade / miss (one shader per chunk)         -> trace segment k (survivors)
+//   SRC_HITS   : hit queue k-1   -> shade (one shader per chunk)                -> trace segment k (survivors)
 //   SRC_RAYS   : caller's rays   (parity entry point pt_trace_rays)             -> trace, results by ray slot
 // Rays never touch HBM: the only stage-to-stage traffic is the hit queue, one 56-byte record per segment,
 // SoA float4, written and read in order:
@@ -246,6 +248,7 @@ struct BounceArgs {
     int segment;              // index k of the segment traced by this launch (shaded hits belong to k-1)
     int max_depth;
     int trace;                // 0: shade only (the launch after the last segment)
+    int drop_last_hits;       // this launch traces the last allowed segment of a scene without emitters (and no G-buffer is due)
     int cam_tiled;            // SRC_CAMERA: width % 8 == 0 and height % 4 == 0, chunks are 8x4 pixel tiles
     int inner_run;            // inner nodes a lane may walk before the warp regroups for primitive tests
     CameraFrame cam;          // SRC_CAMERA
@@ -273,7 +276,7 @@ __device__ __forceinline__ void shade_miss(const BounceArgs& a, float3 d, float3
     if (a.gbuf_normal != nullptr && first_segment) a.gbuf_normal[pid] = make_float4(-d.x, -d.y, -d.z, 0.f);
 }
 
-// Shade (or miss) item `item` of shader bin `bin` of the input hit queue.  Returns true and the next ray when the
+// Shade item `item` of shader bin `bin` of the input hit queue.  Returns true and the next ray when the
 // path goes on; paths that end write their radiance.
 __device__ __forceinline__ bool shade_hit_item(const BounceArgs& a, int bin, uint32_t item, bool last_shade, float3& ray_o,
                                                float3& ray_d, float3& thr, uint32_t& pixel, uint32_t& s) {
@@ -289,7 +292,6 @@ __device__ __forceinline__ bool shade_hit_item(const BounceArgs& a, int bin, uin
     const size_t pid = (size_t)s * a.npix + pixel;
     const float3 o = f3(o4.x, o4.y, o4.z), d = f3(d4.x, d4.y, d4.z);
     thr = f3(t4.x, t4.y, t4.z);
-    if (bin == BIN_MISS) { shade_miss(a, d, thr, pid, a.segment == 1); return false; }
     const uint32_t prim = h.y >> 3;
     const float4 g0 = __ldg(&sc.geo0[prim]);
     const uint32_t mslot = __float_as_uint(__ldg(&sc.geo1[prim]).w) & 0x0fffffffu;
@@ -322,11 +324,12 @@ __device__ __forceinline__ void file_hit(const BounceArgs& a, uint32_t lane, boo
     int obin = -1;
     if (alive)
         obin = (best_code == PT_MISS_CODE) ? BIN_MISS : (int)(__float_as_uint(__ldg(&sc.geo1[best_code >> 3]).w) >> 28);
-#if PT_MISS_INLINE
     // rays that leave the scene end here: the sky is looked up by the lanes that missed instead of sending a
     // 56-byte record through a miss bin to the next launch (v7 did: +9 % on C2 without it)
     if (obin == BIN_MISS) { shade_miss(a, d, thr, (size_t)s * a.npix + pixel, a.segment == 0); obin = -1; }
-#endif
+    // a hit of the last allowed segment can only add emission: in a scene without emitters its path ends black, and
+    // the shade-only launch that would find that out is not enqueued (render_async)
+    if (a.drop_last_hits && obin >= 0) { a.path_out[(size_t)s * a.npix + pixel] = make_float4(0.f, 0.f, 0.f, 0.f); obin = -1; }
     // One atomic INSTRUCTION per chunk: lane b reserves the slots of bin b (up to NUM_BINS lanes issue together, one
     // round trip to L2 instead of one per non-empty bin), then every lane writes its record once.  (v6 looped over
     // the bins: the warp waited for up to five dependent atomics per chunk, 6 % of the stall samples of a bounce

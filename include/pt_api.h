@@ -77,7 +77,8 @@ typedef struct pt_stats {
 } pt_stats;
 
 enum {
-    PT_OPT_WAVE_PATHS = 1,    /* upper bound of paths in flight per wave (default 32 Mi)           */
+    PT_OPT_WAVE_PATHS = 1,    /* upper bound of paths in flight per wave (default 128 Mi = 64 spp at 1080p;
+                                 halved at run time until the hit queues fit in free device memory) */
     PT_OPT_STAGE_TIMING = 2,  /* 1: record per-stage CUDA events (adds syncs at frame end only)    */
     PT_OPT_TIE_ORDER = 3,     /* 1 (default): exactly tied hits resolve in the reference's leaf
                                  visiting order (bvh.cu:31-90,167-205); 0: lowest primitive id wins */

@@ -1,5 +1,6 @@
-"""Profiling target: C2 scene, 1920x1080, 16 spp (= one 33.2 M-path wave) per frame, depth 8.  Same kernels
-and launch shapes as bench.py's step (which is 8 such waves)."""
+"""Profiling target: C2 scene, 1920x1080, 16 spp (= one 33.2 M-path wave) per frame, depth 8.  Same kernels as
+bench.py's step, which is one 64-spp wave (launches four times as long; ncu replays each launch ~40 times, so the
+profile is taken on the quarter-size wave)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cpppathtracer_b200 import api, scenes

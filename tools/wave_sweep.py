@@ -8,7 +8,7 @@ for run in (2, 4, 8):
     r.reset_accum(); r.render(sc.camera, 16, 8, seed=1); r.reset_accum(); r.render(sc.camera, 16, 8, seed=1)
     st = r.stats(); print(f"inner_run {run}: {st['paths']/st['render_ms']/1e3:.1f} Mpaths/s")
 r.set_option(api.PT_OPT_TRAV_INNER_RUN, 4)
-for spp_wave in (1, 2, 4, 8, 16):
+for spp_wave in (1, 2, 4, 8, 16, 32, 64):
     r.set_option(api.PT_OPT_WAVE_PATHS, spp_wave * 1920 * 1080)
     for _ in range(2):
         r.reset_accum(); r.render(sc.camera, 64, 8, seed=1)
