@@ -116,6 +116,8 @@ struct pt_scene {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> stage_events;
     int grid_bounce = 0;
+    uint8_t* disp_host = nullptr;      // pinned BGRA frame handed out by pt_dispatch_ray_frame
+    size_t disp_host_bytes = 0;
     int last_depth = 0;
     size_t stage_events_used = 0;
     bool frame_recorded = false;
@@ -400,10 +402,10 @@ cudaError_t try_reserve_wave(pt_scene* s, uint32_t cap) {
     s->capacity = 0;
     cudaError_t e = s->path_out.reserve(cap);
     for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
-        e = s->hq_o[k].reserve((size_t)NUM_BINS * cap);
-        if (e == cudaSuccess) e = s->hq_d[k].reserve((size_t)NUM_BINS * cap);
-        if (e == cudaSuccess) e = s->hq_thr[k].reserve((size_t)NUM_BINS * cap);
-        if (e == cudaSuccess) e = s->hq_hit[k].reserve((size_t)NUM_BINS * cap);
+        e = s->hq_o[k].reserve((size_t)(NUM_BINS - 1) * cap);
+        if (e == cudaSuccess) e = s->hq_d[k].reserve((size_t)(NUM_BINS - 1) * cap);
+        if (e == cudaSuccess) e = s->hq_thr[k].reserve((size_t)(NUM_BINS - 1) * cap);
+        if (e == cudaSuccess) e = s->hq_hit[k].reserve((size_t)(NUM_BINS - 1) * cap);
     }
     if (e == cudaSuccess) { s->capacity = cap; return e; }
     s->path_out.release();
@@ -656,10 +658,10 @@ void destroy_texture(Texture& t) {
 // cur_sample_idx_ (motional_camera.cu:195): 1 restarts the running mean, like MotionalCamera::Refresh.
 int display_dispatch(pt_scene* s, const pt_camera* cam, int max_depth, uint64_t seed, uint32_t sample_idx,
                      uint8_t* bgra_out, size_t nbytes) {
-    if (!s || !cam || !bgra_out) return fail(PT_ERR_INVALID, "null argument");
+    if (!s || !cam) return fail(PT_ERR_INVALID, "null argument");
     if (sample_idx < 1) return fail(PT_ERR_INVALID, "sample_idx is 1-based");
     const size_t npix = (size_t)cam->width * cam->height;
-    if (nbytes != npix * 4) return fail(PT_ERR_INVALID, "nbytes must be 4*width*height");
+    if (bgra_out != nullptr && nbytes != npix * 4) return fail(PT_ERR_INVALID, "nbytes must be 4*width*height");
     if (cam->width != s->disp_w || cam->height != s->disp_h) {
         s->disp_mix.release(); s->disp_normal.release(); s->disp_bgra.release();
         CK(s->disp_mix.reserve(npix)); CK(s->disp_normal.reserve(npix)); CK(s->disp_bgra.reserve(npix * 4));
@@ -673,6 +675,16 @@ int display_dispatch(pt_scene* s, const pt_camera* cam, int max_depth, uint64_t 
                                             s->disp_bgra.p, (int)sample_idx);
     s->stats.launches += 1;
     CK(cudaGetLastError());
+    if (bgra_out == nullptr) {
+        // library-owned pinned frame (the reference's output_buffer_, path_tracer.cu:303-304): one DMA, no staging
+        if (s->disp_host_bytes < npix * 4) {
+            if (s->disp_host) cudaFreeHost(s->disp_host);
+            s->disp_host = nullptr; s->disp_host_bytes = 0;
+            CK(cudaHostAlloc((void**)&s->disp_host, npix * 4, cudaHostAllocDefault));
+            s->disp_host_bytes = npix * 4;
+        }
+        bgra_out = s->disp_host;
+    }
     CK(cudaMemcpyAsync(bgra_out, s->disp_bgra.p, npix * 4, cudaMemcpyDeviceToHost, s->stream));
     return finish_frame(s, max_depth);
 }
@@ -704,7 +716,8 @@ int pt_scene_create(pt_scene** out) {
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
     if (e != cudaSuccess) {
-        if (s->ev0) cudaEventDestroy(s->ev0);
+        if (s->disp_host) cudaFreeHost(s->disp_host);
+    if (s->ev0) cudaEventDestroy(s->ev0);
         delete s;
         return fail(PT_ERR_CUDA, std::string("pt_scene_create: ") + cudaGetErrorString(e));
     }
@@ -1049,7 +1062,18 @@ int pt_camera_control(pt_camera* cam, int op, float arg, float move_speed) {
 
 int pt_dispatch_ray(pt_scene* s, const pt_camera* cam, int max_depth, uint64_t seed, uint32_t sample_idx,
                     uint8_t* bgra_out, size_t nbytes) {
+    if (!bgra_out) return fail(PT_ERR_INVALID, "null argument");
     return display_dispatch(s, cam, max_depth, seed, sample_idx, bgra_out, nbytes);
+}
+
+int pt_dispatch_ray_frame(pt_scene* s, const pt_camera* cam, int max_depth, uint64_t seed, uint32_t sample_idx,
+                          const uint8_t** bgra, size_t* nbytes) {
+    if (!bgra) return fail(PT_ERR_INVALID, "null argument");
+    int rc = display_dispatch(s, cam, max_depth, seed, sample_idx, nullptr, 0);
+    if (rc) return rc;
+    *bgra = s->disp_host;
+    if (nbytes) *nbytes = (size_t)cam->width * cam->height * 4;
+    return PT_OK;
 }
 
 }  // extern "C"

@@ -14,6 +14,24 @@ namespace pt {
 //             the reference never writes that byte)
 // The 5x5 neighbourhood is addressed as v*width+u and only rejected when that offset leaves the image
 // (path_tracer.cu:212-216), so taps wrap across row ends; reproduced.
+// exp(x) for x <= 0 in double, relative error < 1e-11: range reduction by ln 2 (two-part constant) and a degree-9
+// Taylor polynomial on |r| <= 0.347 (next term r^10/10! < 7e-12).  The reference's weights are
+// `(float)min(exp((double)-d2 / M_PI), 1.0)` (path_tracer.cu:224,228): the library exp is ~90 FP64 operations, and 50
+// of them per pixel made this kernel as long as the whole path trace of the sample (0.52 ms at 1080p).  After the
+// rounding to float this version differs from the correctly rounded value for about 2 weights in 10^4, by one float
+// ulp -- far below what an 8-bit channel can show (tests/test_gpu_display.py pins the bytes to the reference's own
+// kernels; the division by M_PI is a multiplication by its reciprocal, a 1e-16 effect).  Results below half the smallest float denormal are returned as 0, which is what the conversion gives.
+__device__ __forceinline__ double exp_nonpositive(double x) {
+    if (x < -104.0) return 0.0;
+    const double kf = rint(x * 1.4426950408889634);
+    double r = fma(kf, -6.93147180369123816490e-01, x);
+    r = fma(kf, -1.90821492927058770002e-10, r);
+    double p = 1.0 / 362880.0;
+    p = fma(p, r, 1.0 / 40320.0); p = fma(p, r, 1.0 / 5040.0); p = fma(p, r, 1.0 / 720.0); p = fma(p, r, 1.0 / 120.0);
+    p = fma(p, r, 1.0 / 24.0); p = fma(p, r, 1.0 / 6.0); p = fma(p, r, 0.5); p = fma(p, r, 1.0); p = fma(p, r, 1.0);
+    return __longlong_as_double(__double_as_longlong(p) + ((long long)(int)kf << 52));   // 2^k, k >= -151: stays normal
+}
+
 __global__ void __launch_bounds__(256) k_denoise_mix(int width, int height, const float4* __restrict__ color,
                                                      const float4* __restrict__ normal, float4* __restrict__ mix,
                                                      uint8_t* __restrict__ bgra, int cur_sample_idx) {
@@ -40,10 +58,10 @@ __global__ void __launch_bounds__(256) k_denoise_mix(int width, int height, cons
                 ctmp = f3(t4.x, t4.y, t4.z);
                 float3 t = cval - ctmp;
                 float dist2 = dot(t, t);
-                c_w = (float)fmin(exp(-(double)dist2 / PT_PI_D), 1.0);       // exp(-(dist2)/M_PI): double
+                c_w = (float)fmin(exp_nonpositive(-(double)dist2 * (1.0 / PT_PI_D)), 1.0);   // exp(-(dist2)/M_PI): double
                 t = nval - f3(m4.x, m4.y, m4.z);
                 dist2 = fmaxf(dot(t, t), 0.0f);
-                n_w = (float)fmin(exp(-(double)dist2 / PT_PI_D), 1.0);
+                n_w = (float)fmin(exp_nonpositive(-(double)dist2 * (1.0 / PT_PI_D)), 1.0);
                 p_w = 1.0f;                                                   // equal depths: exp(-0/pi)
             }
             const float weight = c_w * n_w * p_w;

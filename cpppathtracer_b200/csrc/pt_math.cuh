@@ -275,9 +275,9 @@ __device__ __forceinline__ void shade_glass(const MaterialRec& m, float3 normal,
     o.radiance = material_emission(m);
 }
 // shader bins (the Metal<->Mirror swap of material.cu:151-156 is applied when the bin is chosen)
-// shader bins of the hit queues.  A ray that leaves the scene never enters a queue (it is shaded by the sky where it
-// ends), so there is no miss bin; BIN_MISS only names that outcome inside file_hit.
-enum { BIN_DIFFUSE = 0, BIN_GLOSSY = 1, BIN_MIX = 2, BIN_GLASS = 3, NUM_BINS = 4, BIN_MISS = 7 };
+// Shader bins.  Bin 0 names the outcome "left the scene": such a ray is shaded by the sky where it ends and never
+// enters a queue, so the hit queues hold NUM_BINS - 1 regions (bin b at region b - 1) and bin 0 stays empty.
+enum { BIN_MISS = 0, BIN_DIFFUSE = 1, BIN_GLOSSY = 2, BIN_MIX = 3, BIN_GLASS = 4, NUM_BINS = 5 };
 __host__ __device__ __forceinline__ int bin_of_material_type(int type) {
     switch (type) {
         case 1: return BIN_GLOSSY;   // MaterialType::Metal  -> MirrorHitShader

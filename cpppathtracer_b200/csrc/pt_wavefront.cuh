@@ -281,7 +281,7 @@ __device__ __forceinline__ void shade_miss(const BounceArgs& a, float3 d, float3
 __device__ __forceinline__ bool shade_hit_item(const BounceArgs& a, int bin, uint32_t item, bool last_shade, float3& ray_o,
                                                float3& ray_d, float3& thr, uint32_t& pixel, uint32_t& s) {
     const SceneDev& sc = a.sc;
-    const size_t q = (size_t)bin * a.hq_in.capacity + item;
+    const size_t q = (size_t)(bin - 1) * a.hq_in.capacity + item;      // bin >= 1: bin 0 (miss) has no queue
     // streamed once: evict-first loads / stores keep the L1 and L2 lines for the BVH nodes
     const float4 o4 = __ldcs(&a.hq_in.o[q]);
     const float4 d4 = __ldcs(&a.hq_in.d[q]);
@@ -292,6 +292,10 @@ __device__ __forceinline__ bool shade_hit_item(const BounceArgs& a, int bin, uin
     const size_t pid = (size_t)s * a.npix + pixel;
     const float3 o = f3(o4.x, o4.y, o4.z), d = f3(d4.x, d4.y, d4.z);
     thr = f3(t4.x, t4.y, t4.z);
+    // Bin 0 has no queue, so this branch is never taken; it stays because ptxas allocates 56 registers with it and 58
+    // without (8 instead of 9 CTAs per SM: -2.2 % on C2, same-box A/B gpurun_out/variants_r2f.log).  The Makefile
+    // checks the register count of this kernel after every build.
+    if (bin == BIN_MISS) { shade_miss(a, d, thr, pid, a.segment == 1); return false; }
     const uint32_t prim = h.y >> 3;
     const float4 g0 = __ldg(&sc.geo0[prim]);
     const uint32_t mslot = __float_as_uint(__ldg(&sc.geo1[prim]).w) & 0x0fffffffu;
@@ -345,7 +349,7 @@ __device__ __forceinline__ void file_hit(const BounceArgs& a, uint32_t lane, boo
     if (lane_mask) base = atomicAdd(&a.ctrl_out->bin_count[lane & 7u].v, (uint32_t)__popc(lane_mask));
     base = __shfl_sync(PT_FULL, base, obin & 7);
     if (obin >= 0) {
-        const size_t j = (size_t)obin * a.hq_out.capacity + base + __popc(my_mask & ((1u << lane) - 1u));
+        const size_t j = (size_t)(obin - 1) * a.hq_out.capacity + base + __popc(my_mask & ((1u << lane) - 1u));
         __stcs(&a.hq_out.o[j], make_float4(o.x, o.y, o.z, __uint_as_float(pixel)));
         __stcs(&a.hq_out.d[j], make_float4(d.x, d.y, d.z, __uint_as_float(s)));
         __stcs(&a.hq_out.thr[j], make_float4(thr.x, thr.y, thr.z, 0.f));

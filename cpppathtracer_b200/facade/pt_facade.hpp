@@ -356,12 +356,14 @@ public:
         if (!scene_ || !camera_) return;
         MotionalCamera cam = camera_->GetCopy();          // increments cur_sample_idx_ like the reference
         pt_camera c = cam.ToAbi();
-        output_.resize((size_t)c.width * c.height * 4);
-        if (pt_dispatch_ray(scene_, &c, max_recursion_depth_, seed_, cam.cur_sample_idx_, output_.data(), output_.size()) != PT_OK) {
+        // the frame lives in the scene's page-locked buffer, valid during the callback like the reference's
+        // output_buffer_ (path_tracer.cu:303-304)
+        const uint8_t* frame = nullptr; size_t nbytes = 0;
+        if (pt_dispatch_ray_frame(scene_, &c, max_recursion_depth_, seed_, cam.cur_sample_idx_, &frame, &nbytes) != PT_OK) {
             err_ = pt_last_error();
             return;
         }
-        if (args.Callback) args.Callback(output_.data(), c.width, c.height, args.cbParam);
+        if (args.Callback) args.Callback(const_cast<uint8_t*>(frame), c.width, c.height, args.cbParam);
     }
 
     // additions (no counterpart in the reference)
@@ -381,7 +383,6 @@ public:
 private:
     pt_scene* scene_ = nullptr;
     std::shared_ptr<MotionalCamera> camera_;
-    std::vector<uint8_t> output_;
     uint8_t max_recursion_depth_ = 8;     // path_tracer.h:43
     uint64_t seed_ = 0;
     std::string err_;

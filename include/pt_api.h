@@ -139,6 +139,11 @@ int pt_get_stats(pt_scene* s, pt_stats* out);
  *      (cuSrc/path_tracer.cu:177-254,285-304).  See pt_dispatch_ray in DESIGN.md. */
 int pt_dispatch_ray(pt_scene* s, const pt_camera* cam, int max_depth, uint64_t seed, uint32_t sample_idx,
                     uint8_t* bgra_out, size_t nbytes);
+/* Same dispatch, but the BGRA8 frame lands in a page-locked buffer OWNED BY THE SCENE (the reference's
+ * PathTracer::output_buffer_, cuSrc/path_tracer.cu:303-304, which its callback receives and must not keep):
+ * *bgra stays valid until the next dispatch on this scene or pt_scene_destroy.  One DMA, no staging copy. */
+int pt_dispatch_ray_frame(pt_scene* s, const pt_camera* cam, int max_depth, uint64_t seed, uint32_t sample_idx,
+                          const uint8_t** bgra, size_t* nbytes);
 
 /* ---- textures: replaces PocaTextureUtils::{AddTexByFile,DestroyTexture} for material textures */
 int pt_texture_create_rgba8(pt_scene* s, const uint8_t* rgba, int width, int height, uint64_t* handle);

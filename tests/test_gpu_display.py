@@ -73,3 +73,15 @@ def test_depth1_dispatch_is_bit_exact(port_oracle, sky):
     assert np.abs(got[..., :3].astype(int) - want[..., :3].astype(int)).max() <= 1
     assert (got[..., :3] == want[..., :3]).mean() > 0.995
     r.close()
+
+
+def test_dispatch_ray_frame_hands_out_the_same_bytes(sky):
+    """pt_dispatch_ray_frame (scene-owned page-locked frame, the reference's output_buffer_) == pt_dispatch_ray."""
+    sc = scenes.sphere_field(300, 256, 144)
+    a, b = api.Renderer(sc, sky), api.Renderer(sc, sky)
+    for idx in (1, 2, 3):
+        want = a.dispatch_ray(sc.camera, idx, max_depth=8, seed=2)
+        got = b.dispatch_ray_frame(sc.camera, idx, max_depth=8, seed=2)
+        assert got.shape == want.shape and got.dtype == np.uint8
+        assert np.array_equal(got, want)
+    a.close(); b.close()

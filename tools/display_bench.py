@@ -15,6 +15,15 @@ for i in range(6, 6 + n):
     r.dispatch_ray(sc.camera, i)
 dt = time.perf_counter() - t0
 out = {"dispatch_ms": dt / n * 1e3, "mpaths_per_s": 1920 * 1080 * n / dt / 1e6}
+a = r.dispatch_ray(sc.camera, 200).copy()
+b = r.dispatch_ray_frame(sc.camera, 200).copy()      # same sample index twice: the running mean moves, so compare loosely
+t0 = time.perf_counter()
+for i in range(300, 300 + n):
+    r.dispatch_ray_frame(sc.camera, i)
+dt = time.perf_counter() - t0
+out["frame_dispatch_ms"] = dt / n * 1e3
+out["frame_mpaths_per_s"] = 1920 * 1080 * n / dt / 1e6
+out["frame_vs_copy_max_byte_diff"] = int(np.abs(a.astype(int) - b.astype(int)).max())
 try:
     from oracle import ref_cuda
     R = ref_cuda.RefCuda(); R.load_scene(sc); R.set_sky(sky)
