@@ -362,11 +362,18 @@ def main():
         hits = st["hit_records"]                   # segments that hit something: the only ones with a queue record
         alg_bytes = ALG_BYTES_PER_SEGMENT * hits + ALG_BYTES_PER_PATH * st["paths"]
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else None
+        # measured DRAM bytes per launch: the ncu capture is taken on a 16-spp wave (tools/profile_target.py; ncu replays
+        # every launch ~40 times), the step here is one 64-spp wave of the same kernels, so the captured bytes of the
+        # wave are scaled by the ratio of the wave sizes and divided by this step's launches
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traverse_traffic.json")
         if os.path.exists(tp):
             with open(tp) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
+                tj = json.load(f)
+            if tj.get("dram_bytes_per_wave") and tj.get("wave_paths"):
+                traffic = tj["dram_bytes_per_wave"] * (st["paths"] / tj["wave_paths"]) / n_launch
+            else:
+                traffic = tj.get("dram_bytes_per_launch")
         line = {
             "metric": METRIC, "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -376,12 +383,13 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "k_bounce (shade previous hits + trace the segment, fused)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                          "traffic": traffic, "peak_source": peak_src,
+                         "traffic_source": "ncu --set full of a 16-spp wave (profiles/traverse_traffic.json), scaled to this step's paths, per launch",
                          "algorithmic_bytes_per_launch": alg_bytes / n_launch, "avg_launch_ms": kern_ms / n_launch,
                          "launches_per_step": n_launch,
                          "share_of_step": kern_ms / st["render_ms"] if st["render_ms"] > 0 else None,
                          "hit_records_per_step": hits,
                          "note": "bound by instruction issue x SIMD efficiency (IPC 2.5-3.2 of 4, 17-30 of 32 lanes active, "
-                                 "long-scoreboard on L1/L2 node fetches; profiles/r01_v8_summary.md), not by HBM; DRAM traffic "
+                                 "long-scoreboard on L1/L2 node fetches; profiles/r01_v11_summary.md), not by HBM; DRAM traffic "
                                  "equals the algorithmic bytes"},
             "path": {"mrays_per_s": segs / (st["render_ms"] * 1e-3) / 1e6 if st["render_ms"] > 0 else None,
                      "segments_per_path": segs / st["paths"], "render_ms_last_frame": st["render_ms"],

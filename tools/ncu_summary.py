@@ -18,7 +18,6 @@ METRICS = [
     ("L2 hit %", "lts__t_sector_hit_rate.pct", 1.0),
     ("DRAM read [GB]", "dram__bytes_read.sum", 1.0),
     ("DRAM write [GB]", "dram__bytes_write.sum", 1.0),
-    ("DRAM % of peak", "FBSP.TriageCompute.dram__throughput.avg.pct_of_peak_sustained_elapsed", 1.0),
     ("FMA pipe %", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", 1.0),
     ("ALU pipe %", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", 1.0),
     ("FP64 pipe %", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", 1.0),
@@ -44,9 +43,10 @@ def raw_page(rep):
         for label, m, _ in METRICS:
             if m not in col:
                 continue
-            if not r[col[m]].strip():
+            try:
+                v, u = float(r[col[m]].replace(",", "")), units[col[m]]
+            except ValueError:      # empty or "no data"
                 continue
-            v, u = float(r[col[m]].replace(",", "")), units[col[m]]
             if m.startswith("dram__bytes"):
                 v *= UNIT_TO_GB.get(u, 1.0)
             if m.startswith("gpu__time"):
@@ -114,6 +114,7 @@ def main():
              "| metric | " + " | ".join(f"seg {i}" for i in range(n)) + " |", "|---|" + "---|" * n]
     for label, _, _ in METRICS:
         lines.append(f"| {label} | " + " | ".join(f"{d.get(label, float('nan')):.4g}" for d in L) + " |")
+    lines.append("| DRAM [GB/s] (read + write) / duration | " + " | ".join(f"{(d['DRAM read [GB]'] + d['DRAM write [GB]']) / (d['duration [ms]'] * 1e-3):.0f}" for d in L) + " |")
     lines.append("| top stall reasons | " + " | ".join(d["stalls"] for d in L) + " |")
     rd, wr = sum(d["DRAM read [GB]"] for d in L), sum(d["DRAM write [GB]"] for d in L)
     lines += ["", f"DRAM traffic of the wave: {rd + wr:.2f} GB (read {rd:.2f}, write {wr:.2f}); sum of durations {sum(d['duration [ms]'] for d in L):.3f} ms.", ""]
@@ -131,6 +132,7 @@ def main():
     if traffic_path:
         per = [(d["DRAM read [GB]"] + d["DRAM write [GB]"]) * 1e9 for d in L]
         json.dump({"kernel": "k_bounce", "dram_bytes_per_launch": sum(per) / n, "per_launch_bytes": per, "launches": n,
+                   "dram_bytes_per_wave": sum(per), "wave_paths": 1920 * 1080 * 16,
                    "source": f"ncu --set full ({rep}), the {n} k_bounce launches of one wave of tools/profile_target.py (C2, 1920x1080, "
                              "16 spp = 33.2 M paths, depth 8): dram__bytes_read.sum + dram__bytes_write.sum"},
                   open(traffic_path, "w"), indent=1)
