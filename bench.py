@@ -401,6 +401,13 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks,
         }
         line["roofline_fp32"] = fp32_view(r, cam, depth, line["path"]["mrays_per_s"], (clocks or {}).get("sm_mhz"))
+        if os.path.exists(tp) and tj.get("ipc_time_weighted"):
+            # third view, from the same ncu capture: what the kernel is actually bound by.  4 warp-instructions can
+            # issue per SM per clock; the capture says how many do and how many of an instruction's 32 lanes are alive.
+            line["roofline_issue"] = {"bound": "warp-instruction issue", "achieved": tj["ipc_time_weighted"], "peak": 4.0,
+                                      "unit": "warp-instructions / clock / SM", "frac": tj["ipc_time_weighted"] / 4.0,
+                                      "active_lanes_of_32": tj["lanes_per_instruction_time_weighted"],
+                                      "source": "ncu --set full of a 16-spp wave (profiles/traverse_traffic.json), time-weighted over its k_bounce launches"}
         if world == 1 and not args.no_baselines:
             line["variants"] = {"libpt_b200_fma.so (nvcc-contracted arithmetic of the reference's CUDA build)": fma_variant_leg(sc, sky)}
             line["cpu_baseline"] = cpu_baseline_leg(sc, sky)

@@ -30,9 +30,6 @@ namespace pt {
 #ifndef PT_PREFETCH_FAR
 #define PT_PREFETCH_FAR 1
 #endif
-#ifndef PT_INNER_UNROLL2
-#define PT_INNER_UNROLL2 0
-#endif
 #ifndef PT_STACK_TOP
 #define PT_STACK_TOP 1
 #endif
@@ -449,15 +446,7 @@ __global__ void PT_BOUNCE_BOUNDS k_bounce(const BounceArgs a) {
                 if (alive) {
                     int k = 0;
 #pragma unroll 1
-#if PT_INNER_UNROLL2
-                    while (r.node >= 0 && r.node != PT_SENTINEL && k < a.inner_run) {
-                        lane_inner(sc, r, stack); if (COUNT_STEPS) { ++n_inner; ++lane_steps; }
-                        if (r.node >= 0 && r.node != PT_SENTINEL) { lane_inner(sc, r, stack); if (COUNT_STEPS) { ++n_inner; ++lane_steps; } }
-                        k += 2;
-                    }
-#else
                     while (r.node >= 0 && r.node != PT_SENTINEL && k < a.inner_run) { lane_inner(sc, r, stack); ++k; if (COUNT_STEPS) { ++n_inner; ++lane_steps; } }
-#endif
                 }
                 if (alive && r.node < 0) { lane_leaf(sc, r, stack); if (COUNT_STEPS) { ++n_leaf; ++lane_steps; } }
             }

@@ -133,6 +133,8 @@ def main():
         per = [(d["DRAM read [GB]"] + d["DRAM write [GB]"]) * 1e9 for d in L]
         json.dump({"kernel": "k_bounce", "dram_bytes_per_launch": sum(per) / n, "per_launch_bytes": per, "launches": n,
                    "dram_bytes_per_wave": sum(per), "wave_paths": 1920 * 1080 * 16,
+                   "ipc_time_weighted": sum(d["IPC (of 4)"] * d["duration [ms]"] for d in L) / sum(d["duration [ms]"] for d in L),
+                   "lanes_per_instruction_time_weighted": sum(d["lanes / instruction"] * d["duration [ms]"] for d in L) / sum(d["duration [ms]"] for d in L),
                    "source": f"ncu --set full ({rep}), the {n} k_bounce launches of one wave of tools/profile_target.py (C2, 1920x1080, "
                              "16 spp = 33.2 M paths, depth 8): dram__bytes_read.sum + dram__bytes_write.sum"},
                   open(traffic_path, "w"), indent=1)
