@@ -80,6 +80,7 @@ struct pt_scene {
     int opt_count_steps = 0;
     int opt_ref_leaf_boxes = 0;
     int opt_inner_run = 4;
+    int opt_sah_passes = 4;        // SAH refit passes (tree rotations) after the Karras build; 0: plain LBVH
     // device scene
     DevBuf<float4> geo0, geo1, nodes, leaf_mn, leaf_mx, leaf_c, inner_mn, inner_mx, test_mn, test_mx;
     DevBuf<MaterialRec> mats;
@@ -117,6 +118,9 @@ struct pt_scene {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> stage_events;
     int grid_bounce = 0;
+    DevBuf<unsigned char> node_height;
+    DevBuf<float> sah_dev;
+    float sah_host[2] = {0.f, 0.f};   // SAH cost (sum of inner areas / root area) before and after the refit passes
     uint8_t* disp_host = nullptr;      // pinned BGRA frame handed out by pt_dispatch_ray_frame
     size_t disp_host_bytes = 0;
     int last_depth = 0;
@@ -362,8 +366,23 @@ int upload_and_build(pt_scene* s) {
             CK(s->cub_tmp.reserve(tmp_bytes + 16));
             CK(cub::DeviceRadixSort::SortPairs(s->cub_tmp.p, tmp_bytes, s->codes.p, s->codes_sorted.p, s->ids.p, s->ids_sorted.p, nt, 0, 30, st));
             k_lbvh_hierarchy<<<gb, tb, 0, st>>>(nt, s->codes_sorted.p, s->children.p, s->parent_inner.p, s->parent_leaf.p);
-            k_lbvh_fit<<<gb, tb, 0, st>>>(nt, s->ids_sorted.p, s->leaf_mn.p, s->leaf_mx.p, s->children.p, s->parent_inner.p,
-                                          s->parent_leaf.p, s->inner_mn.p, s->inner_mx.p, s->flags.p);
+            CK(s->node_height.reserve(nt));
+            LbvhTree tree;
+            tree.sorted_ids = s->ids_sorted.p; tree.leaf_mn = s->leaf_mn.p; tree.leaf_mx = s->leaf_mx.p;
+            tree.children = s->children.p; tree.parent_of_inner = s->parent_inner.p; tree.parent_of_leaf = s->parent_leaf.p;
+            tree.inner_mn = s->inner_mn.p; tree.inner_mx = s->inner_mx.p; tree.height = s->node_height.p;
+            // pass 0 fits the boxes of the Karras tree; every further pass is a SAH refit (tree rotations + fit)
+            for (int pass = 0; pass <= s->opt_sah_passes; ++pass) {
+                if (pass > 0) CK(cudaMemsetAsync(s->flags.p, 0, nt * sizeof(int), st));
+                k_lbvh_fit<<<gb, tb, 0, st>>>(nt, tree, s->flags.p, pass > 0 ? 1 : 0);
+                if (pass == 0 || pass == s->opt_sah_passes) {
+                    CK(s->sah_dev.reserve(2));
+                    if (pass == 0) CK(cudaMemsetAsync(s->sah_dev.p, 0, 2 * sizeof(float), st));
+                    k_lbvh_sah<<<std::min(gb, 256), tb, 0, st>>>(nt, s->inner_mn.p, s->inner_mx.p, s->sah_dev.p + (pass == 0 ? 0 : 1));
+                }
+            }
+            CK(cudaMemcpyAsync(s->sah_host, s->sah_dev.p, 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+            s->stats.launches += (uint64_t)s->opt_sah_passes + 2;
             k_lbvh_pack<<<gb, tb, 0, st>>>(nt, s->ids_sorted.p, s->bvh_prims.p, s->geo1.p, s->leaf_mn.p, s->leaf_mx.p,
                                            s->children.p, s->inner_mn.p, s->inner_mx.p, s->nodes.p);
             s->stats.launches += 5 + 2;   // + the radix sort's own kernels (library), counted as 2
@@ -375,6 +394,8 @@ int upload_and_build(pt_scene* s) {
     CK(cudaEventElapsedTime(&s->stats.build_ms, eb0, eb1));
     cudaEventDestroy(eb0); cudaEventDestroy(eb1);
     s->stats.bvh_nodes = nt > 1 ? (uint32_t)(nt - 1) : (uint32_t)nt;
+    s->stats.bvh_sah_lbvh = nt > 1 ? s->sah_host[0] : 0.f;
+    s->stats.bvh_sah = nt > 1 ? (s->opt_sah_passes > 0 ? s->sah_host[1] : s->sah_host[0]) : 0.f;
     s->dirty = false; s->built = true;
     return PT_OK;
 }
@@ -748,6 +769,7 @@ void pt_scene_destroy(pt_scene* s) {
     s->codes.release(); s->codes_sorted.release(); s->ids.release(); s->ids_sorted.release(); s->bounds6.release();
     s->orig_id.release(); s->cub_tmp.release(); s->accum.release(); s->read_tmp.release(); s->path_out.release(); s->hit.release();
     s->ctrl.release(); s->q_o.release(); s->q_d.release(); s->seg_counter.release();
+    s->node_height.release(); s->sah_dev.release();
     for (int k = 0; k < 2; ++k) { s->hq_o[k].release(); s->hq_d[k].release(); s->hq_thr[k].release(); s->hq_hit[k].release(); s->scratch_i[k].release(); }
     for (auto& b : s->scratch_f) b.release();
     s->disp_color.release(); s->disp_normal.release(); s->disp_mix.release(); s->disp_depth.release(); s->disp_bgra.release();
@@ -768,6 +790,9 @@ int pt_set_option(pt_scene* s, int option, int64_t value) {
         case PT_OPT_SKY_QUARTER_ROWS: s->opt_sky_quarter = value != 0; return PT_OK;
         case PT_OPT_COUNT_STEPS: s->opt_count_steps = value != 0; return PT_OK;
         case PT_OPT_REF_LEAF_BOXES: s->opt_ref_leaf_boxes = value != 0; s->dirty = true; return PT_OK;
+        case PT_OPT_SAH_PASSES:
+            if (value < 0 || value > 16) return fail(PT_ERR_INVALID, "PT_OPT_SAH_PASSES: 0 .. 16");
+            s->opt_sah_passes = (int)value; s->dirty = true; return PT_OK;
         case PT_OPT_TRAV_INNER_RUN:
             if (value < 1 || value > 1024) return fail(PT_ERR_INVALID, "inner_run must be 1..1024");
             s->opt_inner_run = (int)value; return PT_OK;

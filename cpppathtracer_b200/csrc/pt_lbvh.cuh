@@ -169,28 +169,153 @@ __global__ void k_lbvh_hierarchy(int n, const uint32_t* __restrict__ codes, int2
     if (i == 0) parent_of_inner[0] = -1;
 }
 
-// pass 4: bottom-up boxes of the internal nodes; the second thread to arrive at a node fits it
-__global__ void k_lbvh_fit(int n, const uint32_t* __restrict__ sorted_ids, const float4* __restrict__ leaf_mn,
-                           const float4* __restrict__ leaf_mx, const int2* __restrict__ children,
-                           const int* __restrict__ parent_of_inner, const int* __restrict__ parent_of_leaf,
-                           float4* __restrict__ inner_mn, float4* __restrict__ inner_mx, int* __restrict__ flags) {
+// pass 4: bottom-up boxes of the internal nodes; the second thread to arrive at a node fits it.
+//
+// SAH refit (`rotate`): before a node's box is stored, the thread that owns the node -- the only thread alive in its
+// subtree, every other one ended at its first arrival somewhere below -- tries the four tree rotations of Kensler
+// 2008 on it: one child X trades places with a grandchild under the other child Y, which turns Y = (Y1, Y2) into
+// (X, Y2) or (Y1, X).  The node's own box does not change (same leaves); the only surface area that does is Y's, so
+// the rotation with the smallest new area of Y is taken when it beats the current one.  With one primitive per leaf
+// the SAH cost of the tree is the sum of the inner nodes' areas, so every accepted rotation lowers it.  A Karras tree
+// over Morton codes splits where the codes say, not where the boxes are small: the rotations recover most of the
+// distance to a full-sweep SAH build (C2: SAH cost 11.6 -> see DESIGN.md section 3.3) in one or two extra passes of
+// this kernel.  `height` (levels below a node) keeps the walk's stack bound: a rotation that would raise a subtree
+// above PT_LBVH_MAX_ROT_HEIGHT levels is refused unless the subtree was already that high.
+#define PT_LBVH_MAX_ROT_HEIGHT 48
+__device__ __forceinline__ float box_area(float4 mn, float4 mx) {
+    const float dx = mx.x - mn.x, dy = mx.y - mn.y, dz = mx.z - mn.z;
+    return dx * dy + dy * dz + dz * dx;
+}
+__device__ __forceinline__ void box_union(float4 amn, float4 amx, float4 bmn, float4 bmx, float4& mn, float4& mx) {
+    mn = make_float4(fminf(amn.x, bmn.x), fminf(amn.y, bmn.y), fminf(amn.z, bmn.z), 0.f);
+    mx = make_float4(fmaxf(amx.x, bmx.x), fmaxf(amx.y, bmx.y), fmaxf(amx.z, bmx.z), 0.f);
+}
+struct LbvhTree {
+    const uint32_t* sorted_ids; const float4* leaf_mn; const float4* leaf_mx;
+    int2* children; int* parent_of_inner; int* parent_of_leaf;
+    float4* inner_mn; float4* inner_mx; unsigned char* height;
+};
+__device__ __forceinline__ void lbvh_child_box(const LbvhTree& t, int c, float4& mn, float4& mx, int& h) {
+    if (c < 0) { const uint32_t s = t.sorted_ids[~c]; mn = t.leaf_mn[s]; mx = t.leaf_mx[s]; h = 0; }
+    else { mn = __ldcg(&t.inner_mn[c]); mx = __ldcg(&t.inner_mx[c]); h = (int)__ldcg(&t.height[c]); }
+}
+__device__ __forceinline__ void lbvh_set_parent(const LbvhTree& t, int c, int parent) {
+    if (c < 0) t.parent_of_leaf[~c] = parent; else t.parent_of_inner[c] = parent;
+}
+
+__global__ void k_lbvh_fit(int n, LbvhTree t, int* __restrict__ flags, int rotate) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    int node = parent_of_leaf[i];
+    int node = __ldcg(&t.parent_of_leaf[i]);
     while (node >= 0) {
         if (atomicAdd(&flags[node], 1) == 0) return;   // first arrival: the sibling subtree is not done yet
         __threadfence();
-        int2 ch = children[node];
+        int2 ch = __ldcg(&t.children[node]);
         float4 amn, amx, bmn, bmx;
-        if (ch.x < 0) { uint32_t s = sorted_ids[~ch.x]; amn = leaf_mn[s]; amx = leaf_mx[s]; }
-        else { amn = __ldcg(&inner_mn[ch.x]); amx = __ldcg(&inner_mx[ch.x]); }
-        if (ch.y < 0) { uint32_t s = sorted_ids[~ch.y]; bmn = leaf_mn[s]; bmx = leaf_mx[s]; }
-        else { bmn = __ldcg(&inner_mn[ch.y]); bmx = __ldcg(&inner_mx[ch.y]); }
-        inner_mn[node] = make_float4(fminf(amn.x, bmn.x), fminf(amn.y, bmn.y), fminf(amn.z, bmn.z), 0.f);
-        inner_mx[node] = make_float4(fmaxf(amx.x, bmx.x), fmaxf(amx.y, bmx.y), fmaxf(amx.z, bmx.z), 0.f);
+        int ha, hb;
+        lbvh_child_box(t, ch.x, amn, amx, ha);
+        lbvh_child_box(t, ch.y, bmn, bmx, hb);
+        int hnode = 1 + max(ha, hb);
+        if (rotate) {
+            // candidates: (which child is Y, which of its children stays) -> new box of Y
+            float best = 0.f;          // gain in area, > 0 to accept
+            int best_y = -1, best_keep = 0;
+            float4 ymn[2], ymx[2];     // boxes of the grandchildren of the best candidate's Y (scratch per Y)
+            int yh[2] = {0, 0};
+            int2 ych = make_int2(0, 0);
+            float4 kmn = amn, kmx = amx; int2 kch = ch; int kh[2] = {0, 0};
+            for (int y = 0; y < 2; ++y) {
+                const int Y = y == 0 ? ch.x : ch.y;
+                if (Y < 0) continue;                                  // a leaf has no children to trade
+                const float4 xmn = y == 0 ? bmn : amn, xmx = y == 0 ? bmx : amx;   // X = the other child
+                const int hx = y == 0 ? hb : ha;
+                const float area_y = y == 0 ? box_area(amn, amx) : box_area(bmn, bmx);
+                const int2 gc = __ldcg(&t.children[Y]);
+                lbvh_child_box(t, gc.x, ymn[0], ymx[0], yh[0]);
+                lbvh_child_box(t, gc.y, ymn[1], ymx[1], yh[1]);
+                for (int keep = 0; keep < 2; ++keep) {               // Y keeps grandchild `keep`, the other moves up
+                    float4 nmn, nmx;
+                    box_union(ymn[keep], ymx[keep], xmn, xmx, nmn, nmx);
+                    const float gain = area_y - box_area(nmn, nmx);
+                    const int new_hy = 1 + max(yh[keep], hx);
+                    const int new_h = 1 + max(new_hy, yh[1 - keep]);
+                    if (gain > best && new_h <= max(hnode, PT_LBVH_MAX_ROT_HEIGHT)) {
+                        best = gain; best_y = y; best_keep = keep;
+                        kmn = nmn; kmx = nmx; kch = gc; kh[0] = yh[0]; kh[1] = yh[1];
+                    }
+                }
+                ych = gc;
+            }
+            (void)ych;
+            // two more candidates when both children are inner nodes: trade a grandchild of A for one of B
+            // (A1 <-> B1 and A1 <-> B2; the other two pairings are the same trees with the children renamed)
+            int best_swap = -1;
+            int2 ga = make_int2(0, 0), gb2 = make_int2(0, 0);
+            float4 a1mn, a1mx, a2mn, a2mx, b1mn, b1mx, b2mn, b2mx;
+            int ha1 = 0, ha2 = 0, hb1 = 0, hb2 = 0;
+            if (ch.x >= 0 && ch.y >= 0) {
+                ga = __ldcg(&t.children[ch.x]); gb2 = __ldcg(&t.children[ch.y]);
+                lbvh_child_box(t, ga.x, a1mn, a1mx, ha1); lbvh_child_box(t, ga.y, a2mn, a2mx, ha2);
+                lbvh_child_box(t, gb2.x, b1mn, b1mx, hb1); lbvh_child_box(t, gb2.y, b2mn, b2mx, hb2);
+                const float area_ab = box_area(amn, amx) + box_area(bmn, bmx);
+                for (int w = 0; w < 2; ++w) {                        // w = 0: A1 <-> B1, w = 1: A1 <-> B2
+                    float4 pmn, pmx, qmn, qmx;
+                    box_union(w == 0 ? b1mn : b2mn, w == 0 ? b1mx : b2mx, a2mn, a2mx, pmn, pmx);      // A' = (B?, A2)
+                    box_union(a1mn, a1mx, w == 0 ? b2mn : b1mn, w == 0 ? b2mx : b1mx, qmn, qmx);      // B' = (A1, B other)
+                    const float gain = area_ab - box_area(pmn, pmx) - box_area(qmn, qmx);
+                    const int nha = 1 + max(w == 0 ? hb1 : hb2, ha2), nhb = 1 + max(ha1, w == 0 ? hb2 : hb1);
+                    if (gain > best && 1 + max(nha, nhb) <= max(hnode, PT_LBVH_MAX_ROT_HEIGHT)) { best = gain; best_swap = w; best_y = -1; }
+                }
+            }
+            if (best_swap >= 0) {
+                const int A = ch.x, B = ch.y;
+                const int moved_to_a = best_swap == 0 ? gb2.x : gb2.y, stays_in_b = best_swap == 0 ? gb2.y : gb2.x;
+                float4 pmn, pmx, qmn, qmx;
+                box_union(best_swap == 0 ? b1mn : b2mn, best_swap == 0 ? b1mx : b2mx, a2mn, a2mx, pmn, pmx);
+                box_union(a1mn, a1mx, best_swap == 0 ? b2mn : b1mn, best_swap == 0 ? b2mx : b1mx, qmn, qmx);
+                t.children[A] = make_int2(moved_to_a, ga.y);
+                t.children[B] = make_int2(ga.x, stays_in_b);
+                t.inner_mn[A] = pmn; t.inner_mx[A] = pmx; t.inner_mn[B] = qmn; t.inner_mx[B] = qmx;
+                const int nha = 1 + max(best_swap == 0 ? hb1 : hb2, ha2), nhb = 1 + max(ha1, best_swap == 0 ? hb2 : hb1);
+                t.height[A] = (unsigned char)nha; t.height[B] = (unsigned char)nhb;
+                lbvh_set_parent(t, moved_to_a, A);
+                lbvh_set_parent(t, ga.x, B);
+                hnode = 1 + max(nha, nhb);
+            }
+            if (best_y >= 0) {
+                const int Y = best_y == 0 ? ch.x : ch.y;
+                const int X = best_y == 0 ? ch.y : ch.x;
+                const int hx = best_y == 0 ? hb : ha;
+                const int kept = best_keep == 0 ? kch.x : kch.y;
+                const int up = best_keep == 0 ? kch.y : kch.x;
+                // Y = (kept, X), node = (up, Y)
+                t.children[Y] = make_int2(kept, X);
+                t.inner_mn[Y] = kmn; t.inner_mx[Y] = kmx;
+                const int new_hy = 1 + max(kh[best_keep], hx);
+                t.height[Y] = (unsigned char)new_hy;
+                lbvh_set_parent(t, X, Y);
+                lbvh_set_parent(t, up, node);
+                ch = make_int2(up, Y);
+                t.children[node] = ch;
+                hnode = 1 + max(new_hy, kh[1 - best_keep]);
+            }
+        }
+        float4 nmn, nmx;
+        box_union(amn, amx, bmn, bmx, nmn, nmx);      // the same leaves before and after a rotation
+        t.inner_mn[node] = nmn; t.inner_mx[node] = nmx;
+        t.height[node] = (unsigned char)min(hnode, 255);
         __threadfence();
-        node = parent_of_inner[node];
+        node = __ldcg(&t.parent_of_inner[node]);
     }
+}
+
+// SAH cost of the tree relative to the root's area: sum of the inner nodes' areas / area(root) (one primitive per leaf)
+__global__ void k_lbvh_sah(int n, const float4* __restrict__ inner_mn, const float4* __restrict__ inner_mx, float* __restrict__ out) {
+    float acc = 0.f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n - 1; i += gridDim.x * blockDim.x) acc += box_area(inner_mn[i], inner_mx[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, acc / fmaxf(box_area(inner_mn[0], inner_mx[0]), 1e-30f));
 }
 
 __device__ __forceinline__ void centre_half(float4 mn, float4 mx, float3& c, float3& h) {

@@ -74,6 +74,8 @@ typedef struct pt_stats {
     uint64_t node_steps;      /* inner BVH nodes visited (only with PT_OPT_COUNT_STEPS)       */
     uint64_t prim_tests;      /* sphere / cylinder tests run (only with PT_OPT_COUNT_STEPS)   */
     uint64_t hit_records;     /* 56-byte hit records that went through the hit queues (segments that hit) */
+    float    bvh_sah_lbvh;    /* SAH cost (sum of inner-node areas / root area) of the Karras tree ...        */
+    float    bvh_sah;         /* ... and after the SAH refit passes (PT_OPT_SAH_PASSES)                        */
 } pt_stats;
 
 enum {
@@ -88,7 +90,8 @@ enum {
                                    tree is hit, like SceneBVH::TraceRay does (bvh.cu:175-180); removes most of the
                                    long-range graze-class differences at the price of more primitive tests. default 0 */
     PT_OPT_COUNT_STEPS = 8,     /* 1: use the instrumented traversal kernel that counts node visits / primitive tests */
-    PT_OPT_TRAV_INNER_RUN = 7   /* tuning: inner-node steps a lane may take before the warp regroups for leaf tests */
+    PT_OPT_TRAV_INNER_RUN = 7,  /* tuning: inner-node steps a lane may take before the warp regroups for leaf tests */
+    PT_OPT_SAH_PASSES = 10      /* SAH refit passes (tree rotations) after the LBVH build; default 4, 0 = plain LBVH */
 };
 
 /* ---- lifetime -------------------------------------------------------------------------------- */

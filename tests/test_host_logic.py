@@ -56,7 +56,7 @@ def test_product_does_not_touch_oracle():
 
 def test_struct_layouts_match_header():
     assert C.sizeof(api.PtMaterial) == 48 and C.sizeof(api.PtCamera) == 52
-    assert C.sizeof(api.PtStats) == 80
+    assert C.sizeof(api.PtStats) == 88
 
 
 def test_scene_generators_are_deterministic():
