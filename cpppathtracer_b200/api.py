@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libpt_b200.so")          # default: uncontracted
 LIB_PATH_FMA = os.path.join(_HERE, "libpt_b200_fma.so")  # nvcc-contracted arithmetic == the reference's CUDA build
 
 PT_OPT_WAVE_PATHS, PT_OPT_STAGE_TIMING, PT_OPT_TIE_ORDER, PT_OPT_SKY_QUARTER_ROWS = 1, 2, 3, 4
-PT_OPT_TRAV_INNER_RUN, PT_OPT_COUNT_STEPS, PT_OPT_REF_LEAF_BOXES, PT_OPT_SAH_PASSES = 7, 8, 9, 10
+PT_OPT_TRAV_INNER_RUN, PT_OPT_COUNT_STEPS, PT_OPT_REF_LEAF_BOXES, PT_OPT_SAH_PASSES, PT_OPT_SAH_TREELETS = 7, 8, 9, 10, 11
 
 
 class PtMaterial(C.Structure):

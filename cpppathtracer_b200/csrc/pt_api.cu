@@ -80,6 +80,7 @@ struct pt_scene {
     int opt_count_steps = 0;
     int opt_ref_leaf_boxes = 0;
     int opt_inner_run = 4;
+    int opt_sah_treelets = 0;      // 1: the refit passes restructure 7-leaf treelets by dynamic programming (slower build, lower SAH)
     int opt_sah_passes = 4;        // SAH refit passes (tree rotations) after the Karras build; 0: plain LBVH
     // device scene
     DevBuf<float4> geo0, geo1, nodes, leaf_mn, leaf_mx, leaf_c, inner_mn, inner_mx, test_mn, test_mx;
@@ -374,7 +375,7 @@ int upload_and_build(pt_scene* s) {
             // pass 0 fits the boxes of the Karras tree; every further pass is a SAH refit (tree rotations + fit)
             for (int pass = 0; pass <= s->opt_sah_passes; ++pass) {
                 if (pass > 0) CK(cudaMemsetAsync(s->flags.p, 0, nt * sizeof(int), st));
-                k_lbvh_fit<<<gb, tb, 0, st>>>(nt, tree, s->flags.p, pass > 0 ? 1 : 0);
+                k_lbvh_fit<<<gb, tb, 0, st>>>(nt, tree, s->flags.p, pass > 0 ? (s->opt_sah_treelets ? 2 : 1) : 0);
                 if (pass == 0 || pass == s->opt_sah_passes) {
                     CK(s->sah_dev.reserve(2));
                     if (pass == 0) CK(cudaMemsetAsync(s->sah_dev.p, 0, 2 * sizeof(float), st));
@@ -790,6 +791,7 @@ int pt_set_option(pt_scene* s, int option, int64_t value) {
         case PT_OPT_SKY_QUARTER_ROWS: s->opt_sky_quarter = value != 0; return PT_OK;
         case PT_OPT_COUNT_STEPS: s->opt_count_steps = value != 0; return PT_OK;
         case PT_OPT_REF_LEAF_BOXES: s->opt_ref_leaf_boxes = value != 0; s->dirty = true; return PT_OK;
+        case PT_OPT_SAH_TREELETS: s->opt_sah_treelets = value != 0; s->dirty = true; return PT_OK;
         case PT_OPT_SAH_PASSES:
             if (value < 0 || value > 16) return fail(PT_ERR_INVALID, "PT_OPT_SAH_PASSES: 0 .. 16");
             s->opt_sah_passes = (int)value; s->dirty = true; return PT_OK;

@@ -203,6 +203,107 @@ __device__ __forceinline__ void lbvh_set_parent(const LbvhTree& t, int c, int pa
     if (c < 0) t.parent_of_leaf[~c] = parent; else t.parent_of_inner[c] = parent;
 }
 
+// Treelet restructuring (Karras & Aila 2013, one thread per treelet): the subtree top under `node` is grown into a
+// treelet of up to 7 "leaves" (always expanding the leaf with the largest area), the binary tree over those leaves
+// with the smallest sum of inner areas is found by dynamic programming over the 2^7 subsets, and the treelet's inner
+// nodes are rewired to it when it beats the current arrangement.  Subtrees below the treelet leaves are untouched, so
+// their cost is a constant; the treelet root keeps its box.  Returns the new height of `node`.
+#define PT_TREELET 7
+__device__ int lbvh_treelet_optimize(const LbvhTree& t, int node, int2 ch, int old_height) {
+    int leaf[PT_TREELET];            // treelet leaves: tree links (inner >= 0, leaf < 0)
+    float4 lmn[PT_TREELET], lmx[PT_TREELET];
+    int lh[PT_TREELET];
+    int inner[PT_TREELET - 1];       // inner nodes of the treelet, root first
+    int n_leaf = 2, n_inner = 1;
+    inner[0] = node;
+    leaf[0] = ch.x; leaf[1] = ch.y;
+    lbvh_child_box(t, ch.x, lmn[0], lmx[0], lh[0]);
+    lbvh_child_box(t, ch.y, lmn[1], lmx[1], lh[1]);
+    float old_cost = 0.f;            // sum of the areas of the treelet's inner nodes except the root
+    while (n_leaf < PT_TREELET) {
+        int pick = -1; float pa = -1.f;
+        for (int i = 0; i < n_leaf; ++i)
+            if (leaf[i] >= 0) { const float a = box_area(lmn[i], lmx[i]); if (a > pa) { pa = a; pick = i; } }
+        if (pick < 0) break;
+        const int x = leaf[pick];
+        old_cost += pa;
+        inner[n_inner++] = x;
+        const int2 c = __ldcg(&t.children[x]);
+        leaf[pick] = c.x; lbvh_child_box(t, c.x, lmn[pick], lmx[pick], lh[pick]);
+        leaf[n_leaf] = c.y; lbvh_child_box(t, c.y, lmn[n_leaf], lmx[n_leaf], lh[n_leaf]);
+        ++n_leaf;
+    }
+    if (n_leaf < 3) return old_height;
+    const int full = (1 << n_leaf) - 1;
+    float area[1 << PT_TREELET], cost[1 << PT_TREELET];
+    unsigned char part[1 << PT_TREELET];
+    for (int s = 1; s <= full; ++s) {
+        float4 mn = make_float4(3e38f, 3e38f, 3e38f, 0.f), mx = make_float4(-3e38f, -3e38f, -3e38f, 0.f);
+        for (int i = 0; i < n_leaf; ++i)
+            if (s >> i & 1) box_union(mn, mx, lmn[i], lmx[i], mn, mx);
+        area[s] = box_area(mn, mx);
+    }
+    // subsets in increasing numeric order: every proper subset of s is smaller than s
+    for (int s = 1; s <= full; ++s) {
+        if ((s & (s - 1)) == 0) { cost[s] = 0.f; part[s] = 0; continue; }
+        const int low = s & -s;
+        float best = 3e38f; int bp = 0;
+        for (int p = (s - 1) & s; p > 0; p = (p - 1) & s) {
+            if (!(p & low)) continue;                       // each split once: the half that holds the lowest leaf
+            const float c = cost[p] + cost[s ^ p];
+            if (c < best) { best = c; bp = p; }
+        }
+        cost[s] = best + (s == full ? 0.f : area[s]);
+        part[s] = (unsigned char)bp;
+    }
+    if (!(cost[full] < old_cost * 0.99999f)) return old_height;
+    // rebuild: a stack of (subset, node slot); slot 0 is the treelet root
+    int stack_s[PT_TREELET], stack_n[PT_TREELET], sp = 0, next_inner = 1;
+    // heights need the children first: record the build order and finish bottom-up
+    int order_s[PT_TREELET - 1], order_n[PT_TREELET - 1], n_order = 0;
+    int2 new_ch[PT_TREELET - 1];
+    stack_s[sp] = full; stack_n[sp] = inner[0]; ++sp;
+    while (sp > 0) {
+        --sp;
+        const int s = stack_s[sp], nd = stack_n[sp];
+        const int halves[2] = {(int)part[s], s ^ (int)part[s]};
+        int links[2];
+        for (int k = 0; k < 2; ++k) {
+            const int h = halves[k];
+            if ((h & (h - 1)) == 0) links[k] = leaf[__ffs(h) - 1];
+            else { links[k] = inner[next_inner++]; stack_s[sp] = h; stack_n[sp] = links[k]; ++sp; }
+        }
+        order_s[n_order] = s; order_n[n_order] = nd; new_ch[n_order] = make_int2(links[0], links[1]); ++n_order;
+    }
+    // heights of the new inner nodes, children before parents (reverse build order), and the height test
+    int new_h[PT_TREELET - 1];
+    for (int k = n_order - 1; k >= 0; --k) {
+        int hh[2];
+        const int links[2] = {new_ch[k].x, new_ch[k].y};
+        for (int c = 0; c < 2; ++c) {
+            hh[c] = -1;
+            for (int i = 0; i < n_leaf; ++i) if (leaf[i] == links[c]) hh[c] = lh[i];
+            if (hh[c] < 0) for (int j = k + 1; j < n_order; ++j) if (order_n[j] == links[c]) hh[c] = new_h[j];
+        }
+        new_h[k] = 1 + max(hh[0], hh[1]);
+    }
+    if (new_h[0] > max(old_height, PT_LBVH_MAX_ROT_HEIGHT)) return old_height;
+    for (int k = n_order - 1; k >= 0; --k) {
+        const int nd = order_n[k], s = order_s[k];
+        t.children[nd] = new_ch[k];
+        lbvh_set_parent(t, new_ch[k].x, nd);
+        lbvh_set_parent(t, new_ch[k].y, nd);
+        t.height[nd] = (unsigned char)min(new_h[k], 255);
+        if (k > 0) {                                        // the root's box is written by the caller
+            float4 mn = make_float4(3e38f, 3e38f, 3e38f, 0.f), mx = make_float4(-3e38f, -3e38f, -3e38f, 0.f);
+            for (int i = 0; i < n_leaf; ++i)
+                if (s >> i & 1) box_union(mn, mx, lmn[i], lmx[i], mn, mx);
+            t.inner_mn[nd] = mn; t.inner_mx[nd] = mx;
+        }
+    }
+    return new_h[0];
+}
+
 __global__ void k_lbvh_fit(int n, LbvhTree t, int* __restrict__ flags, int rotate) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -216,7 +317,9 @@ __global__ void k_lbvh_fit(int n, LbvhTree t, int* __restrict__ flags, int rotat
         lbvh_child_box(t, ch.x, amn, amx, ha);
         lbvh_child_box(t, ch.y, bmn, bmx, hb);
         int hnode = 1 + max(ha, hb);
-        if (rotate) {
+        if (rotate == 2) {
+            hnode = lbvh_treelet_optimize(t, node, ch, hnode);
+        } else if (rotate) {
             // candidates: (which child is Y, which of its children stays) -> new box of Y
             float best = 0.f;          // gain in area, > 0 to accept
             int best_y = -1, best_keep = 0;

@@ -54,9 +54,9 @@ def test_sah_refit_lowers_cost_and_keeps_every_hit(maker, sky):
     tree over the same primitives (every primitive is still found by rays aimed at it)."""
     sc = maker()
     out = {}
-    for passes in (0, 4):
+    for passes in (0, 4, -2):                                       # -2: two passes of treelet restructuring
         r = api.Renderer(sc, sky)
-        r.set_option(api.PT_OPT_SAH_PASSES, passes); r.build()
+        r.set_option(api.PT_OPT_SAH_PASSES, abs(passes)); r.set_option(api.PT_OPT_SAH_TREELETS, int(passes < 0)); r.build()
         r.render(sc.camera, 4, 8, seed=3)
         img = r.read_accum().copy(); st = r.stats()
         rng = np.random.RandomState(1)
@@ -76,3 +76,6 @@ def test_sah_refit_lowers_cost_and_keeps_every_hit(maker, sky):
     assert np.array_equal(img0, img4)
     assert st4["bvh_sah_lbvh"] == pytest.approx(st0["bvh_sah_lbvh"], rel=1e-4) and st0["bvh_sah"] == st0["bvh_sah_lbvh"]
     assert st4["bvh_sah"] < st4["bvh_sah_lbvh"] and v4 < v0
+    imgt, primt, tt, stt, vt = out[-2]
+    assert np.array_equal(prim0, primt) and np.array_equal(t0, tt) and np.array_equal(img0, imgt)
+    assert stt["bvh_sah"] < st4["bvh_sah"] and vt < v0
