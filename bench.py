@@ -389,7 +389,7 @@ def main():
                          "share_of_step": kern_ms / st["render_ms"] if st["render_ms"] > 0 else None,
                          "hit_records_per_step": hits,
                          "note": "bound by instruction issue x SIMD efficiency (IPC 2.5-3.2 of 4, 17-30 of 32 lanes active, "
-                                 "long-scoreboard on L1/L2 node fetches; profiles/r01_v11_summary.md), not by HBM; DRAM traffic "
+                                 "long-scoreboard on L1/L2 node fetches; profiles/r01_v12_summary.md), not by HBM; DRAM traffic "
                                  "equals the algorithmic bytes"},
             "path": {"mrays_per_s": segs / (st["render_ms"] * 1e-3) / 1e6 if st["render_ms"] > 0 else None,
                      "segments_per_path": segs / st["paths"], "render_ms_last_frame": st["render_ms"],
