@@ -347,16 +347,18 @@ def test_reference_cuda_kernels_agree(sky):
     r.close()
 
 
-def test_level3_converged_image_1024spp(oracle, sky):
-    """Convergence of the image error with spp: RMSE falls as 1/sqrt(spp) from the per-sample 1.0e-2, so the
-    north_star bound (1e-3 at 4096 spp, i.e. <= 2e-3 at 1024 spp) is met with margin; channel means within 0.5 %."""
-    sc = scenes.demo_scene(160, 90)
-    img, ref, st, ost = _render_pair(sc, sky, oracle, 1024, seed=23)
+@pytest.mark.parametrize("w,h,spp,bound", [(160, 90, 1024, 1.0e-3), (96, 54, 4096, 5.0e-4)])
+def test_level3_converged_image(w, h, spp, bound, oracle, sky):
+    """Convergence of the image error with spp: RMSE falls as 1/sqrt(spp) from the per-sample 1.0e-2.  north_star asks
+    for RMSE <= 1e-3 and channel means within 0.5 % at 4096 spp: met at 1024 spp already, and with a factor of two to
+    spare at 4096 spp (the demo scene, every material, the sky)."""
+    sc = scenes.demo_scene(w, h)
+    img, ref, st, ost = _render_pair(sc, sky, oracle, spp, seed=23)
     rmse = float(np.sqrt(np.mean((img[..., :3] - ref) ** 2)))
-    assert rmse <= 1.0e-3, f"rmse at 1024 spp {rmse:.3e}"
+    assert rmse <= bound, f"rmse at {spp} spp {rmse:.3e}"
     gm, rm = img[..., :3].mean(axis=(0, 1)), ref.mean(axis=(0, 1))
     assert np.all(np.abs(gm - rm) <= 0.005 * rm)
-    print(f"1024 spp: rmse {rmse:.3e}, means {gm} vs {rm}")
+    print(f"{spp} spp: rmse {rmse:.3e}, means {gm} vs {rm}")
 
 
 def test_full_size_stress_scene_c3(oracle, port_oracle, sky):
