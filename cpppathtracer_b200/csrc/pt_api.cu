@@ -73,7 +73,7 @@ struct pt_scene {
     bool dirty = true, built = false;
     // options
     uint32_t opt_wave_paths = 128u << 20;  // 64 spp per wave at 1080p: 59 GB of hit queues; 5.57 vs 5.40 Gpaths/s with 32 Mi (16 spp), 5.23 with 16 Mi
-                                           // (gpurun_out/wave_sweep_v9.log); ensure_queues halves the wave until the queues fit in free memory
+                                           // (profiles/ab/wave_sweep_v9.log); ensure_queues halves the wave until the queues fit in free memory
     int opt_stage_timing = 0;
     int opt_tie_order = 1;
     int opt_sky_quarter = 1;

@@ -293,7 +293,7 @@ __device__ __forceinline__ bool shade_hit_item(const BounceArgs& a, int bin, uin
     const float3 o = f3(o4.x, o4.y, o4.z), d = f3(d4.x, d4.y, d4.z);
     thr = f3(t4.x, t4.y, t4.z);
     // Bin 0 has no queue, so this branch is never taken; it stays because ptxas allocates 56 registers with it and 58
-    // without (8 instead of 9 CTAs per SM: -2.2 % on C2, same-box A/B gpurun_out/variants_r2f.log).  The Makefile
+    // without (8 instead of 9 CTAs per SM: -2.2 % on C2, same-box A/B profiles/ab/variants_r2f.log).  The Makefile
     // checks the register count of this kernel after every build.
     if (bin == BIN_MISS) { shade_miss(a, d, thr, pid, a.segment == 1); return false; }
     const uint32_t prim = h.y >> 3;
