@@ -156,7 +156,8 @@ int pt_texture_create_rgba8(pt_scene* s, const uint8_t* rgba, int width, int hei
 int pt_texture_destroy(pt_scene* s, uint64_t handle);
 
 /* ---- image files: replaces cv::imread + cvtColor(CV_BGR2RGBA) of AddTexByFile (cuSrc/textures.cu:15-17).
- *      8-bit non-interlaced PNG (grey, grey+alpha, RGB, RGBA, palette) -> malloc'ed RGBA8 rows; host only. */
+ *      Any PNG colour type / bit depth, sequential or Adam7 -> malloc'ed RGBA8 rows (16-bit samples keep their high
+ *      byte, 1/2/4-bit grey is scaled to 0..255, like imread's 8-bit conversion); host only. */
 int pt_image_load_png(const char* path, uint8_t** rgba_out, int* width, int* height);
 void pt_image_free(uint8_t* rgba);
 

@@ -146,8 +146,78 @@ def test_png_loader_matches_pil(tmp_path):
     bad.write_bytes(b"not a png at all" * 4)
     with pytest.raises(api.PtError):
         api.load_png(str(bad))
-    Image.fromarray((rng.rand(8, 8) * 65535).astype(np.uint16)).save(str(tmp_path / "deep.png"))
-    with pytest.raises(api.PtError):
-        api.load_png(str(tmp_path / "deep.png"))
     with pytest.raises(api.PtError):
         api.load_png(str(tmp_path / "missing.png"))
+
+
+def _write_png(path, samples, ctype, depth, interlace, palette=None):
+    """Minimal PNG writer for the loader test: samples [h, w, channels] (ints < 2**depth), filter type 0, optional Adam7."""
+    import struct, zlib
+    h, w, ch = samples.shape
+
+    def pack_rows(img):
+        rows = []
+        for row in img:
+            flat = row.reshape(-1).astype(np.uint32)
+            if depth == 16:
+                b = np.stack([flat >> 8, flat & 255], 1).astype(np.uint8).tobytes()
+            elif depth == 8:
+                b = flat.astype(np.uint8).tobytes()
+            else:
+                bits = np.zeros(((len(flat) * depth + 7) // 8) * 8, np.uint8)
+                for k in range(depth):
+                    bits[np.arange(len(flat)) * depth + k] = (flat >> (depth - 1 - k)) & 1
+                b = np.packbits(bits).tobytes()
+            rows.append(b"\x00" + b)
+        return b"".join(rows)
+
+    passes = [(0, 0, 8, 8), (4, 0, 8, 8), (0, 4, 4, 8), (2, 0, 4, 4), (0, 2, 2, 4), (1, 0, 2, 2), (0, 1, 1, 2)] if interlace else [(0, 0, 1, 1)]
+    raw = b"".join(pack_rows(samples[ys::yst, xs::xst]) for xs, ys, xst, yst in passes if samples[ys::yst, xs::xst].size)
+
+    def chunk(tag, data):
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xffffffff)
+    out = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, 1 if interlace else 0))
+    if palette is not None:
+        out += chunk(b"PLTE", palette.astype(np.uint8).tobytes())
+    out += chunk(b"IDAT", zlib.compress(raw)) + chunk(b"IEND", b"")
+    open(path, "wb").write(out)
+
+
+@pytest.mark.parametrize("interlace", [0, 1])
+def test_png_loader_every_depth_and_adam7(tmp_path, interlace):
+    """Bit depths 1/2/4/16 and Adam7 interlacing: 16-bit samples keep their high byte and low-depth grey is scaled to
+    0..255 -- the 8-bit image cv::imread hands the reference (textures.cu:15); cross-checked with cv2 when it is there."""
+    rng = np.random.RandomState(9)
+    h, w = 19, 23                                                  # odd sizes: ragged Adam7 passes and ragged packed rows
+    cases = []
+    for depth in (1, 2, 4, 8, 16):
+        cases.append(("grey", 0, depth, rng.randint(0, 2 ** depth, (h, w, 1))))
+    for depth in (8, 16):
+        cases += [("rgb", 2, depth, rng.randint(0, 2 ** depth, (h, w, 3))), ("rgba", 6, depth, rng.randint(0, 2 ** depth, (h, w, 4))),
+                  ("la", 4, depth, rng.randint(0, 2 ** depth, (h, w, 2)))]
+    pal = rng.randint(0, 256, (16, 3))
+    for depth in (1, 2, 4, 8):
+        cases.append(("pal", 3, depth, rng.randint(0, min(2 ** depth, 16), (h, w, 1))))
+    for name, ctype, depth, smp in cases:
+        path = str(tmp_path / f"{name}{depth}_{interlace}.png")
+        _write_png(path, smp, ctype, depth, interlace, palette=pal if ctype == 3 else None)
+        got = api.load_png(path)
+        s8 = (smp >> 8) if depth == 16 else smp
+        if ctype == 0:
+            g = (s8[..., 0] * 255 // (2 ** min(depth, 8) - 1)) if depth < 8 else s8[..., 0]
+            want = np.dstack([g, g, g, np.full_like(g, 255)])
+        elif ctype == 2:
+            want = np.dstack([s8, np.full((h, w, 1), 255)])
+        elif ctype == 6:
+            want = s8
+        elif ctype == 4:
+            want = np.dstack([s8[..., 0], s8[..., 0], s8[..., 0], s8[..., 1]])
+        else:
+            want = np.dstack([pal[smp[..., 0]], np.full((h, w, 1), 255)])
+        assert got.shape == (h, w, 4) and np.array_equal(got, want.astype(np.uint8)), (name, depth, interlace)
+        try:
+            import cv2
+        except ImportError:
+            continue
+        bgr = cv2.imread(path)                                      # what the reference's loader starts from
+        assert bgr is not None and np.array_equal(bgr[..., ::-1], got[..., :3]), (name, depth, interlace, "cv2")
