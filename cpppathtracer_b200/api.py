@@ -43,7 +43,7 @@ EXPORTS = [
     "pt_scene_create", "pt_scene_destroy", "pt_set_option", "pt_set_stream", "pt_add_sphere", "pt_add_platform",
     "pt_add_cylinder", "pt_set_material", "pt_update_prim", "pt_set_sky_rgba8", "pt_build", "pt_render_frame",
     "pt_render_frame_async", "pt_synchronize", "pt_reset_accum", "pt_read_accum", "pt_accum_device_ptr",
-    "pt_get_stats", "pt_dispatch_ray", "pt_dispatch_ray_frame", "pt_texture_create_rgba8", "pt_texture_destroy", "pt_trace_rays", "pt_last_trace_steps",
+    "pt_get_stats", "pt_dispatch_ray", "pt_dispatch_ray_frame", "pt_dispatch_ray_begin", "pt_dispatch_ray_end", "pt_texture_create_rgba8", "pt_texture_destroy", "pt_trace_rays", "pt_last_trace_steps",
     "pt_shade_batch", "pt_raygen_batch", "pt_sky_lookup", "pt_philox_uniforms", "pt_camera_basis", "pt_camera_control",
     "pt_last_error",
     "pt_version", "pt_image_load_png", "pt_image_free",
@@ -83,6 +83,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
                                     C.c_size_t]
     lib.pt_dispatch_ray_frame.argtypes = [C.c_void_p, C.POINTER(PtCamera), C.c_int, C.c_uint64, C.c_uint32,
                                           C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_size_t)]
+    lib.pt_dispatch_ray_begin.argtypes = [C.c_void_p, C.POINTER(PtCamera), C.c_int, C.c_uint64, C.c_uint32]
+    lib.pt_dispatch_ray_end.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_size_t)]
     lib.pt_trace_rays.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
     lib.pt_shade_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 9
     lib.pt_raygen_batch.argtypes = [C.c_void_p, C.POINTER(PtCamera), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -286,6 +288,18 @@ class Renderer:
         self._check(self.lib.pt_dispatch_ray_frame(self.h, C.byref(c), int(max_depth), int(seed), int(sample_idx),
                                                    C.byref(ptr), C.byref(nbytes)))
         return np.ctypeslib.as_array(ptr, shape=(cam.height, cam.width, 4))
+
+    def dispatch_ray_begin(self, cam, sample_idx: int, max_depth: int = 8, seed: int = 0):
+        """First half of a pipelined dispatch (at most two in flight); pair with dispatch_ray_end."""
+        c = to_pt_camera(cam)
+        self._check(self.lib.pt_dispatch_ray_begin(self.h, C.byref(c), int(max_depth), int(seed), int(sample_idx)))
+        self._pipe_shapes = getattr(self, "_pipe_shapes", []) + [(cam.height, cam.width, 4)]
+
+    def dispatch_ray_end(self) -> np.ndarray:
+        """Second half: a VIEW of the oldest frame begun (valid until the second begin after it)."""
+        ptr, nbytes = C.POINTER(C.c_uint8)(), C.c_size_t(0)
+        self._check(self.lib.pt_dispatch_ray_end(self.h, C.byref(ptr), C.byref(nbytes)))
+        return np.ctypeslib.as_array(ptr, shape=self._pipe_shapes.pop(0))
 
     # -- parity entry points ----------------------------------------------------------------------------
     def trace(self, rays8: np.ndarray):

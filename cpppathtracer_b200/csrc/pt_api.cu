@@ -124,6 +124,14 @@ struct pt_scene {
     float sah_host[2] = {0.f, 0.f};   // SAH cost (sum of inner areas / root area) before and after the refit passes
     uint8_t* disp_host = nullptr;      // pinned BGRA frame handed out by pt_dispatch_ray_frame
     size_t disp_host_bytes = 0;
+    // pipelined dispatch (pt_dispatch_ray_begin / _end): two frames in flight, the D2H copy of one on its own stream
+    // under the trace of the next
+    DevBuf<uint8_t> pipe_bgra[2];
+    uint8_t* pipe_host[2] = {nullptr, nullptr};
+    size_t pipe_bytes = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t pipe_filtered[2] = {nullptr, nullptr}, pipe_copied[2] = {nullptr, nullptr};
+    uint64_t pipe_begun = 0, pipe_ended = 0;
     int last_depth = 0;
     size_t stage_events_used = 0;
     bool frame_recorded = false;
@@ -688,12 +696,9 @@ void destroy_texture(Texture& t) {
 // One iteration of the reference's PipelineLoop (cuSrc/path_tracer.cu:256-306) minus the host thread:
 // one sample per pixel -> Denoising -> Mix -> BGRA8 -> D2H.  sample_idx is the reference's 1-based
 // cur_sample_idx_ (motional_camera.cu:195): 1 restarts the running mean, like MotionalCamera::Refresh.
-int display_dispatch(pt_scene* s, const pt_camera* cam, int max_depth, uint64_t seed, uint32_t sample_idx,
-                     uint8_t* bgra_out, size_t nbytes) {
-    if (!s || !cam) return fail(PT_ERR_INVALID, "null argument");
-    if (sample_idx < 1) return fail(PT_ERR_INVALID, "sample_idx is 1-based");
+// trace one sample and run the fused filter + mix + pack into `bgra_dev` (device), all on the scene's stream
+int display_sample(pt_scene* s, const pt_camera* cam, int max_depth, uint64_t seed, uint32_t sample_idx, uint8_t* bgra_dev) {
     const size_t npix = (size_t)cam->width * cam->height;
-    if (bgra_out != nullptr && nbytes != npix * 4) return fail(PT_ERR_INVALID, "nbytes must be 4*width*height");
     if (cam->width != s->disp_w || cam->height != s->disp_h) {
         s->disp_mix.release(); s->disp_normal.release(); s->disp_bgra.release();
         CK(s->disp_mix.reserve(npix)); CK(s->disp_normal.reserve(npix)); CK(s->disp_bgra.reserve(npix * 4));
@@ -704,13 +709,31 @@ int display_dispatch(pt_scene* s, const pt_camera* cam, int max_depth, uint64_t 
     if (rc) return rc;
     dim3 tb(32, 8), gb((cam->width + 31) / 32, (cam->height + 7) / 8);
     k_denoise_mix<<<gb, tb, 0, s->stream>>>(cam->width, cam->height, s->path_out.p, s->disp_normal.p, s->disp_mix.p,
-                                            s->disp_bgra.p, (int)sample_idx);
+                                            bgra_dev ? bgra_dev : s->disp_bgra.p, (int)sample_idx);
     s->stats.launches += 1;
     CK(cudaGetLastError());
+    return PT_OK;
+}
+
+int display_dispatch(pt_scene* s, const pt_camera* cam, int max_depth, uint64_t seed, uint32_t sample_idx,
+                     uint8_t* bgra_out, size_t nbytes) {
+    if (!s || !cam) return fail(PT_ERR_INVALID, "null argument");
+    if (sample_idx < 1) return fail(PT_ERR_INVALID, "sample_idx is 1-based");
+    const size_t npix = (size_t)cam->width * cam->height;
+    if (bgra_out != nullptr && nbytes != npix * 4) return fail(PT_ERR_INVALID, "nbytes must be 4*width*height");
+    int rc = display_sample(s, cam, max_depth, seed, sample_idx, nullptr);
+    if (rc) return rc;
     if (bgra_out == nullptr) {
         // library-owned pinned frame (the reference's output_buffer_, path_tracer.cu:303-304): one DMA, no staging
         if (s->disp_host_bytes < npix * 4) {
             if (s->disp_host) cudaFreeHost(s->disp_host);
+    if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); cudaStreamDestroy(s->copy_stream); }
+    for (int k = 0; k < 2; ++k) {
+        if (s->pipe_host[k]) cudaFreeHost(s->pipe_host[k]);
+        s->pipe_bgra[k].release();
+        if (s->pipe_filtered[k]) cudaEventDestroy(s->pipe_filtered[k]);
+        if (s->pipe_copied[k]) cudaEventDestroy(s->pipe_copied[k]);
+    }
             s->disp_host = nullptr; s->disp_host_bytes = 0;
             CK(cudaHostAlloc((void**)&s->disp_host, npix * 4, cudaHostAllocDefault));
             s->disp_host_bytes = npix * 4;
@@ -719,6 +742,53 @@ int display_dispatch(pt_scene* s, const pt_camera* cam, int max_depth, uint64_t 
     }
     CK(cudaMemcpyAsync(bgra_out, s->disp_bgra.p, npix * 4, cudaMemcpyDeviceToHost, s->stream));
     return finish_frame(s, max_depth);
+}
+
+// Pipelined dispatch.  The reference's DispatchRay is asynchronous (a task queue drained by a render thread that
+// calls back, path_tracer.cu:256-319); here the asynchrony is two calls: _begin enqueues sample + filter + mix on the
+// scene's stream and the D2H copy of the frame on a copy stream, _end waits for the OLDEST frame begun and hands out
+// its page-locked buffer.  With one frame always in flight (begin(i+1) before end(i)) the copy and the host's
+// callback run under the trace of the next sample.
+int display_begin(pt_scene* s, const pt_camera* cam, int max_depth, uint64_t seed, uint32_t sample_idx) {
+    if (!s || !cam) return fail(PT_ERR_INVALID, "null argument");
+    if (sample_idx < 1) return fail(PT_ERR_INVALID, "sample_idx is 1-based");
+    if (s->pipe_begun - s->pipe_ended >= 2) return fail(PT_ERR_INVALID, "two dispatches are already in flight: call pt_dispatch_ray_end first");
+    const size_t bytes = (size_t)cam->width * cam->height * 4;
+    if (s->pipe_bytes != bytes) {
+        if (s->pipe_begun != s->pipe_ended) return fail(PT_ERR_INVALID, "frame size changed with a dispatch in flight");
+        for (int k = 0; k < 2; ++k) {
+            if (s->pipe_host[k]) cudaFreeHost(s->pipe_host[k]);
+            s->pipe_host[k] = nullptr;
+            CK(s->pipe_bgra[k].reserve(bytes));
+            CK(cudaHostAlloc((void**)&s->pipe_host[k], bytes, cudaHostAllocDefault));
+            if (!s->pipe_filtered[k]) CK(cudaEventCreateWithFlags(&s->pipe_filtered[k], cudaEventDisableTiming));
+            if (!s->pipe_copied[k]) CK(cudaEventCreateWithFlags(&s->pipe_copied[k], cudaEventDisableTiming));
+        }
+        if (!s->copy_stream) CK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+        s->pipe_bytes = bytes;
+    }
+    const int k = (int)(s->pipe_begun & 1);
+    // the filter of this dispatch overwrites device frame k: its previous copy must have left the device
+    if (s->pipe_begun >= 2) CK(cudaStreamWaitEvent(s->stream, s->pipe_copied[k], 0));
+    int rc = display_sample(s, cam, max_depth, seed, sample_idx, s->pipe_bgra[k].p);
+    if (rc) return rc;
+    CK(cudaEventRecord(s->pipe_filtered[k], s->stream));
+    CK(cudaStreamWaitEvent(s->copy_stream, s->pipe_filtered[k], 0));
+    CK(cudaMemcpyAsync(s->pipe_host[k], s->pipe_bgra[k].p, bytes, cudaMemcpyDeviceToHost, s->copy_stream));
+    CK(cudaEventRecord(s->pipe_copied[k], s->copy_stream));
+    s->frame_recorded = false;       // no per-frame statistics in this mode (they need a stream synchronisation)
+    ++s->pipe_begun;
+    return PT_OK;
+}
+int display_end(pt_scene* s, const uint8_t** bgra, size_t* nbytes) {
+    if (!s || !bgra) return fail(PT_ERR_INVALID, "null argument");
+    if (s->pipe_begun == s->pipe_ended) return fail(PT_ERR_INVALID, "no dispatch in flight");
+    const int k = (int)(s->pipe_ended & 1);
+    CK(cudaEventSynchronize(s->pipe_copied[k]));
+    *bgra = s->pipe_host[k];
+    if (nbytes) *nbytes = s->pipe_bytes;
+    ++s->pipe_ended;
+    return PT_OK;
 }
 
 }  // namespace
@@ -1102,6 +1172,11 @@ int pt_dispatch_ray(pt_scene* s, const pt_camera* cam, int max_depth, uint64_t s
     if (!bgra_out) return fail(PT_ERR_INVALID, "null argument");
     return display_dispatch(s, cam, max_depth, seed, sample_idx, bgra_out, nbytes);
 }
+
+int pt_dispatch_ray_begin(pt_scene* s, const pt_camera* cam, int max_depth, uint64_t seed, uint32_t sample_idx) {
+    return display_begin(s, cam, max_depth, seed, sample_idx);
+}
+int pt_dispatch_ray_end(pt_scene* s, const uint8_t** bgra, size_t* nbytes) { return display_end(s, bgra, nbytes); }
 
 int pt_dispatch_ray_frame(pt_scene* s, const pt_camera* cam, int max_depth, uint64_t seed, uint32_t sample_idx,
                           const uint8_t** bgra, size_t* nbytes) {

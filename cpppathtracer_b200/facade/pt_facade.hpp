@@ -327,8 +327,9 @@ private:
 // section: path_tracer.h
 // Facade of include/path_tracer.h:15-26: the class VideoRenderer drives (cppSrc/video_renderer.cpp:33-38,81,119,163).
 // Same five methods.  Differences, all documented in INTEGRATION.md:
-//   * DispatchRay is synchronous: it renders one sample, filters, mixes, copies the BGRA frame to the host and
-//     calls args.Callback before returning (the reference does this on a detached thread, path_tracer.cu:256-306);
+//   * DispatchRay is synchronous by default: it renders one sample, filters, mixes, copies the BGRA frame to the host
+//     and calls args.Callback before returning (the reference does this on a detached thread, path_tracer.cu:256-306);
+//     SetPipelined(true) makes it asynchronous -- the callback of a dispatch runs inside the next one (or Flush);
 //   * errors are kept in LastError() instead of a log file;
 //   * the sky comes from SetSkyRgba8() instead of a hard-wired "textures\\sky.png" (path_tracer.cu:47).
 #include <memory>
@@ -341,7 +342,7 @@ private:
 class PathTracer {
 public:
     PathTracer() { if (pt_scene_create(&scene_) != PT_OK) { scene_ = nullptr; err_ = pt_last_error(); } SceneBVH::Bind(scene_); }
-    ~PathTracer() { if (scene_) pt_scene_destroy(scene_); SceneBVH::ReleaseBVH(); SceneBVH::Bind(nullptr); }
+    ~PathTracer() { if (scene_) { Flush(); pt_scene_destroy(scene_); } SceneBVH::ReleaseBVH(); SceneBVH::Bind(nullptr); }
     PathTracer(const PathTracer&) = delete;
     PathTracer& operator=(const PathTracer&) = delete;
 
@@ -356,6 +357,15 @@ public:
         if (!scene_ || !camera_) return;
         MotionalCamera cam = camera_->GetCopy();          // increments cur_sample_idx_ like the reference
         pt_camera c = cam.ToAbi();
+        if (pipelined_) {
+            // asynchronous like the reference (task queue + render thread, path_tracer.cu:256-319), without a thread: the
+            // sample is enqueued and the call returns; its callback runs inside the NEXT DispatchRay (or Flush), by when
+            // its frame has been copied under that next sample's trace
+            if (pt_dispatch_ray_begin(scene_, &c, max_recursion_depth_, seed_, cam.cur_sample_idx_) != PT_OK) { err_ = pt_last_error(); return; }
+            pending_.push_back(Pending{args, c.width, c.height});
+            if (pending_.size() == 2) DeliverOldest();
+            return;
+        }
         // the frame lives in the scene's page-locked buffer, valid during the callback like the reference's
         // output_buffer_ (path_tracer.cu:303-304)
         const uint8_t* frame = nullptr; size_t nbytes = 0;
@@ -376,11 +386,24 @@ public:
         pt_image_free(px);
         return ok;
     }
+    // pipelined DispatchRay (see there); Flush delivers the frames still in flight
+    void SetPipelined(bool on) { if (!on) Flush(); pipelined_ = on; }
+    void Flush() { while (!pending_.empty()) DeliverOldest(); }
     void SetSeed(uint64_t seed) { seed_ = seed; }
     pt_scene* Handle() { return scene_; }
     const std::string& LastError() const { return err_; }
 
 private:
+    struct Pending { DispatchRayArgs args; int width, height; };
+    void DeliverOldest() {
+        const uint8_t* frame = nullptr; size_t nbytes = 0;
+        const Pending p = pending_.front();
+        pending_.erase(pending_.begin());
+        if (pt_dispatch_ray_end(scene_, &frame, &nbytes) != PT_OK) { err_ = pt_last_error(); return; }
+        if (p.args.Callback) p.args.Callback(const_cast<uint8_t*>(frame), p.width, p.height, p.args.cbParam);
+    }
+    std::vector<Pending> pending_;
+    bool pipelined_ = false;
     pt_scene* scene_ = nullptr;
     std::shared_ptr<MotionalCamera> camera_;
     uint8_t max_recursion_depth_ = 8;     // path_tracer.h:43

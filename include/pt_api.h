@@ -150,6 +150,13 @@ int pt_dispatch_ray(pt_scene* s, const pt_camera* cam, int max_depth, uint64_t s
  * *bgra stays valid until the next dispatch on this scene or pt_scene_destroy.  One DMA, no staging copy. */
 int pt_dispatch_ray_frame(pt_scene* s, const pt_camera* cam, int max_depth, uint64_t seed, uint32_t sample_idx,
                           const uint8_t** bgra, size_t* nbytes);
+/* The same dispatch in two halves, for the reference's ASYNCHRONOUS use of DispatchRay (a task queue drained by a render
+ * thread that calls back, cuSrc/path_tracer.cu:256-319): _begin enqueues sample + Denoising + Mix and the D2H copy of
+ * the frame and returns; _end waits for the oldest frame begun and hands out its page-locked buffer (valid until the
+ * second _begin after it).  At most two dispatches may be in flight; begin(i+1) before end(i) hides the copy and the
+ * caller's work on frame i under the trace of sample i+1.  pt_get_stats is not updated by these calls. */
+int pt_dispatch_ray_begin(pt_scene* s, const pt_camera* cam, int max_depth, uint64_t seed, uint32_t sample_idx);
+int pt_dispatch_ray_end(pt_scene* s, const uint8_t** bgra, size_t* nbytes);
 
 /* ---- textures: replaces PocaTextureUtils::{AddTexByFile,DestroyTexture} for material textures */
 int pt_texture_create_rgba8(pt_scene* s, const uint8_t* rgba, int width, int height, uint64_t* handle);

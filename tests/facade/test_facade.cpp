@@ -63,5 +63,15 @@ int main() {
     std::thread t([&] { tracer->DispatchRay(args); });
     t.join();
     printf("threaded frames %d\n", fr.calls);
+
+    // pipelined mode: the callback of dispatch i runs inside dispatch i+1; Flush delivers the last one
+    const int base = fr.calls;
+    tracer->SetPipelined(true);
+    tracer->DispatchRay(args); const int after1 = fr.calls - base;
+    tracer->DispatchRay(args); const int after2 = fr.calls - base;
+    tracer->DispatchRay(args); const int after3 = fr.calls - base;
+    tracer->Flush();
+    printf("pipelined %d %d %d %d err '%s'\n", after1, after2, after3, fr.calls - base, tracer->LastError().c_str());
+    tracer->SetPipelined(false);
     return 0;
 }

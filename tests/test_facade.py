@@ -60,6 +60,8 @@ def test_facade_driver_end_to_end(tmp_path):
     assert out[2].startswith("after_move idx 1 changed 1")
     assert out[3] == "after_update changed 1"
     assert out[4] == "threaded frames 7"
+    # pipelined DispatchRay: no callback after the first dispatch, one per dispatch afterwards, the last at Flush
+    assert out[5] == "pipelined 0 1 2 3 err ''"
 
 
 def _compile_c(src, out):

@@ -85,3 +85,23 @@ def test_dispatch_ray_frame_hands_out_the_same_bytes(sky):
         assert got.shape == want.shape and got.dtype == np.uint8
         assert np.array_equal(got, want)
     a.close(); b.close()
+
+
+def test_pipelined_dispatch_delivers_the_same_frames_in_order(sky):
+    """pt_dispatch_ray_begin / _end (two frames in flight, D2H on a copy stream) == pt_dispatch_ray, frame by frame."""
+    sc = scenes.sphere_field(300, 256, 144)
+    a, b = api.Renderer(sc, sky), api.Renderer(sc, sky)
+    want = [a.dispatch_ray(sc.camera, idx, max_depth=8, seed=2).copy() for idx in range(1, 7)]
+    got = []
+    b.dispatch_ray_begin(sc.camera, 1, max_depth=8, seed=2)
+    for idx in range(2, 7):
+        b.dispatch_ray_begin(sc.camera, idx, max_depth=8, seed=2)      # sample idx is traced while frame idx-1 is copied
+        got.append(b.dispatch_ray_end().copy())
+    with pytest.raises(api.PtError):                                     # one in flight + two more = three: refused
+        b.dispatch_ray_begin(sc.camera, 7, 8, 2); b.dispatch_ray_begin(sc.camera, 8, 8, 2)
+    got.append(b.dispatch_ray_end().copy())
+    b.dispatch_ray_end()                                                 # the frame of sample 7
+    with pytest.raises(api.PtError):
+        b.dispatch_ray_end()                                             # nothing in flight
+    assert len(got) == 6 and all(np.array_equal(g, w) for g, w in zip(got, want))
+    a.close(); b.close()

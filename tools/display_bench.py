@@ -23,6 +23,15 @@ for i in range(300, 300 + n):
 dt = time.perf_counter() - t0
 out["frame_dispatch_ms"] = dt / n * 1e3
 out["frame_mpaths_per_s"] = 1920 * 1080 * n / dt / 1e6
+r.dispatch_ray_begin(sc.camera, 400)
+t0 = time.perf_counter()
+for i in range(401, 401 + n):
+    r.dispatch_ray_begin(sc.camera, i)
+    r.dispatch_ray_end()
+dt = time.perf_counter() - t0
+r.dispatch_ray_end()
+out["pipelined_dispatch_ms"] = dt / n * 1e3
+out["pipelined_mpaths_per_s"] = 1920 * 1080 * n / dt / 1e6
 out["frame_vs_copy_max_byte_diff"] = int(np.abs(a.astype(int) - b.astype(int)).max())
 try:
     from oracle import ref_cuda
