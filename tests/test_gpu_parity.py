@@ -167,6 +167,37 @@ def test_level1_edge_scenes(oracle, sky):
     r.close()
 
 
+@pytest.mark.parametrize("treelets", [0, 1])
+def test_level1_coincident_primitives_and_sah_refit(treelets, oracle, sky):
+    """Equal Morton codes and exactly coinciding boxes (100 copies of one sphere, 50 of one cylinder, among 250 random
+    primitives): the Karras tie-break by index, the SAH refit (rotations / treelets with zero-gain candidates) and the
+    reference's tie order must still give the reference's closest hit on every ray."""
+    base = scenes.demo_scene(32, 18)
+    rng = np.random.RandomState(4)
+    n_rand = 250
+    types = [scenes.PLATFORM] + [scenes.SPHERE] * 100 + [scenes.CYLINDER] * 50 + list(rng.choice([scenes.SPHERE, scenes.CYLINDER], n_rand))
+    centers = [[0, 0, 0]] + [[3.0, 2.0, -1.0]] * 100 + [[-6.0, 1.5, 4.0]] * 50 + (rng.uniform(-20, 20, (n_rand, 3)) * [1, 0, 1] + [0, 2, 0]).tolist()
+    radii = [0] + [2.0] * 100 + [1.5] * 50 + rng.uniform(0.3, 2.0, n_rand).tolist()
+    heights = [0] + [0] * 100 + [3.0] * 50 + rng.uniform(0.5, 4.0, n_rand).tolist()
+    sc = scenes.demo_scene(32, 18)
+    sc.prim_type = np.array(types, np.int32); sc.center = np.array(centers, np.float32).reshape(-1, 3)
+    sc.radius = np.array(radii, np.float32); sc.y_pos = np.zeros(len(types), np.float32)
+    sc.height = np.array(heights, np.float32); sc.mat_idx = (np.arange(len(types)) % len(base.materials)).astype(np.int32)
+    sc.materials = base.materials
+    r = api.Renderer(sc, sky)
+    r.set_option(api.PT_OPT_SAH_TREELETS, treelets); r.build()
+    oracle.load_scene(sc)
+    o = rng.uniform(-25, 25, (20000, 3)).astype(np.float32); o[:, 1] = rng.uniform(0.1, 30, 20000)
+    target = sc.center[rng.randint(1, len(types), 20000)] + rng.normal(size=(20000, 3)).astype(np.float32)
+    d = target - o; d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([o, d, np.full((20000, 1), 2e-5, np.float32), np.full((20000, 1), 1e30, np.float32)], 1).astype(np.float32)
+    mism, exact = _check_trace(r, oracle, rays)
+    assert mism == 0 and exact > 0.999
+    st = r.stats()
+    assert st["bvh_sah"] <= st["bvh_sah_lbvh"]
+    r.close()
+
+
 def test_level1_ties_follow_reference_leaf_order(oracle, sky):
     """Cylinder bottom caps coincide with the floor plane (video_renderer.cpp:78,105-106): rays from inside a
     cylinder towards the floor hit both at exactly the same t; the winner must be the reference's."""
