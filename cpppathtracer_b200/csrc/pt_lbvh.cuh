@@ -208,7 +208,9 @@ __device__ __forceinline__ void lbvh_set_parent(const LbvhTree& t, int c, int pa
 // with the smallest sum of inner areas is found by dynamic programming over the 2^7 subsets, and the treelet's inner
 // nodes are rewired to it when it beats the current arrangement.  Subtrees below the treelet leaves are untouched, so
 // their cost is a constant; the treelet root keeps its box.  Returns the new height of `node`.
+#ifndef PT_TREELET
 #define PT_TREELET 7
+#endif
 __device__ int lbvh_treelet_optimize(const LbvhTree& t, int node, int2 ch, int old_height) {
     int leaf[PT_TREELET];            // treelet leaves: tree links (inner >= 0, leaf < 0)
     float4 lmn[PT_TREELET], lmx[PT_TREELET];
