@@ -42,7 +42,7 @@ class PtStats(C.Structure):
 EXPORTS = [
     "pt_scene_create", "pt_scene_destroy", "pt_set_option", "pt_set_stream", "pt_add_sphere", "pt_add_platform",
     "pt_add_cylinder", "pt_set_material", "pt_update_prim", "pt_set_sky_rgba8", "pt_build", "pt_render_frame",
-    "pt_render_frame_async", "pt_synchronize", "pt_reset_accum", "pt_read_accum", "pt_accum_device_ptr",
+    "pt_render_frame_async", "pt_synchronize", "pt_reset_accum", "pt_ensure_frame", "pt_read_accum", "pt_accum_device_ptr",
     "pt_get_stats", "pt_dispatch_ray", "pt_dispatch_ray_frame", "pt_dispatch_ray_begin", "pt_dispatch_ray_end", "pt_texture_create_rgba8", "pt_texture_destroy", "pt_trace_rays", "pt_last_trace_steps",
     "pt_shade_batch", "pt_raygen_batch", "pt_sky_lookup", "pt_philox_uniforms", "pt_camera_basis", "pt_camera_control",
     "pt_last_error",
@@ -78,6 +78,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.pt_render_frame.argtypes = [C.c_void_p, C.POINTER(PtCamera), C.c_int, C.c_int, C.c_uint64, C.c_uint32]
     lib.pt_render_frame_async.argtypes = lib.pt_render_frame.argtypes
     lib.pt_read_accum.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.pt_ensure_frame.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.pt_set_sky_rgba8.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     lib.pt_dispatch_ray.argtypes = [C.c_void_p, C.POINTER(PtCamera), C.c_int, C.c_uint64, C.c_uint32, C.c_void_p,
                                     C.c_size_t]
@@ -166,6 +167,7 @@ class Renderer:
         h = C.c_void_p()
         self._check(self.lib.pt_scene_create(C.byref(h)))
         self.h = h
+        self.stream_ptr = 0
         self.n_prims = 0
         if scene is not None:
             self.load_scene(scene)
@@ -228,6 +230,7 @@ class Renderer:
 
     def set_stream(self, cuda_stream: int):
         self._check(self.lib.pt_set_stream(self.h, C.c_void_p(int(cuda_stream))))
+        self.stream_ptr = int(cuda_stream)
 
     def set_sky(self, rgba: np.ndarray):
         rgba = np.ascontiguousarray(rgba, np.uint8)
@@ -253,6 +256,11 @@ class Renderer:
 
     def synchronize(self):
         self._check(self.lib.pt_synchronize(self.h))
+
+    def ensure_frame(self, width: int, height: int):
+        """Allocate (zeroed) the SUM buffer for a width x height frame without rendering into it."""
+        self._check(self.lib.pt_ensure_frame(self.h, int(width), int(height)))
+        self._wh = (int(width), int(height))
 
     def reset_accum(self):
         self._check(self.lib.pt_reset_accum(self.h))

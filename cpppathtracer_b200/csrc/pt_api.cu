@@ -46,6 +46,19 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
 };
 
+// Every entry point that touches a scene runs on the device the scene was created on, whatever the calling thread's
+// current device is (one process driving several GPUs, a host application that switches devices), and restores it.
+struct DeviceGuard {
+    int prev = -1; bool switched = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define PT_ON_SCENE_DEVICE(s) DeviceGuard pt_device_guard_((s) ? (s)->device : 0)
+
 struct HostPrim {
     int type;
     float c[3];
@@ -693,6 +706,24 @@ void destroy_texture(Texture& t) {
     t.obj = 0; t.arr = nullptr;
 }
 
+// Frees everything the display path holds on the host side or on the copy stream, and leaves every handle null so
+// that the next dispatch allocates afresh.  Called by pt_scene_destroy (and only there: the buffers handed to the
+// caller stay valid for the scene's lifetime unless a dispatch replaces them).
+void release_display_host(pt_scene* s) {
+    if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); cudaStreamDestroy(s->copy_stream); s->copy_stream = nullptr; }
+    for (int k = 0; k < 2; ++k) {
+        if (s->pipe_host[k]) cudaFreeHost(s->pipe_host[k]);
+        s->pipe_host[k] = nullptr;
+        s->pipe_bgra[k].release();
+        if (s->pipe_filtered[k]) cudaEventDestroy(s->pipe_filtered[k]);
+        if (s->pipe_copied[k]) cudaEventDestroy(s->pipe_copied[k]);
+        s->pipe_filtered[k] = s->pipe_copied[k] = nullptr;
+    }
+    s->pipe_bytes = 0; s->pipe_begun = s->pipe_ended = 0;
+    if (s->disp_host) cudaFreeHost(s->disp_host);
+    s->disp_host = nullptr; s->disp_host_bytes = 0;
+}
+
 // One iteration of the reference's PipelineLoop (cuSrc/path_tracer.cu:256-306) minus the host thread:
 // one sample per pixel -> Denoising -> Mix -> BGRA8 -> D2H.  sample_idx is the reference's 1-based
 // cur_sample_idx_ (motional_camera.cu:195): 1 restarts the running mean, like MotionalCamera::Refresh.
@@ -726,14 +757,9 @@ int display_dispatch(pt_scene* s, const pt_camera* cam, int max_depth, uint64_t 
     if (bgra_out == nullptr) {
         // library-owned pinned frame (the reference's output_buffer_, path_tracer.cu:303-304): one DMA, no staging
         if (s->disp_host_bytes < npix * 4) {
+            // the previous frame may still be the target of an in-flight copy only if the caller broke the contract
+            // (the buffer is valid until the next dispatch); the stream is idle here (finish_frame synchronised it)
             if (s->disp_host) cudaFreeHost(s->disp_host);
-    if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); cudaStreamDestroy(s->copy_stream); }
-    for (int k = 0; k < 2; ++k) {
-        if (s->pipe_host[k]) cudaFreeHost(s->pipe_host[k]);
-        s->pipe_bgra[k].release();
-        if (s->pipe_filtered[k]) cudaEventDestroy(s->pipe_filtered[k]);
-        if (s->pipe_copied[k]) cudaEventDestroy(s->pipe_copied[k]);
-    }
             s->disp_host = nullptr; s->disp_host_bytes = 0;
             CK(cudaHostAlloc((void**)&s->disp_host, npix * 4, cudaHostAllocDefault));
             s->disp_host_bytes = npix * 4;
@@ -756,6 +782,7 @@ int display_begin(pt_scene* s, const pt_camera* cam, int max_depth, uint64_t see
     const size_t bytes = (size_t)cam->width * cam->height * 4;
     if (s->pipe_bytes != bytes) {
         if (s->pipe_begun != s->pipe_ended) return fail(PT_ERR_INVALID, "frame size changed with a dispatch in flight");
+        s->pipe_bytes = 0;          // a failure below must not leave the old size paired with freed buffers
         for (int k = 0; k < 2; ++k) {
             if (s->pipe_host[k]) cudaFreeHost(s->pipe_host[k]);
             s->pipe_host[k] = nullptr;
@@ -818,8 +845,8 @@ int pt_scene_create(pt_scene** out) {
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
     if (e != cudaSuccess) {
-        if (s->disp_host) cudaFreeHost(s->disp_host);
-    if (s->ev0) cudaEventDestroy(s->ev0);
+        if (s->ev0) cudaEventDestroy(s->ev0);
+        if (s->ev1) cudaEventDestroy(s->ev1);
         delete s;
         return fail(PT_ERR_CUDA, std::string("pt_scene_create: ") + cudaGetErrorString(e));
     }
@@ -829,6 +856,7 @@ int pt_scene_create(pt_scene** out) {
 }
 
 void pt_scene_destroy(pt_scene* s) {
+    PT_ON_SCENE_DEVICE(s);
     if (!s) return;
     cudaStreamSynchronize(s->stream);
     destroy_texture(s->sky);
@@ -844,6 +872,9 @@ void pt_scene_destroy(pt_scene* s) {
     for (int k = 0; k < 2; ++k) { s->hq_o[k].release(); s->hq_d[k].release(); s->hq_thr[k].release(); s->hq_hit[k].release(); s->scratch_i[k].release(); }
     for (auto& b : s->scratch_f) b.release();
     s->disp_color.release(); s->disp_normal.release(); s->disp_mix.release(); s->disp_depth.release(); s->disp_bgra.release();
+    // display path: the scene-owned page-locked frames (the reference's output_buffer_, path_tracer.cu:303-304, lives as
+    // long as its PathTracer) and the copy stream / events of the pipelined dispatch
+    release_display_host(s);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     for (auto e : s->stage_events) cudaEventDestroy(e);
@@ -918,6 +949,7 @@ int pt_update_prim(pt_scene* s, int prim, const float center[3], float radius, f
 }
 
 int pt_set_sky_rgba8(pt_scene* s, const uint8_t* rgba, int width, int height) {
+    PT_ON_SCENE_DEVICE(s);
     if (!s) return fail(PT_ERR_INVALID, "null scene");
     CK(cudaStreamSynchronize(s->stream));
     destroy_texture(s->sky);
@@ -926,6 +958,7 @@ int pt_set_sky_rgba8(pt_scene* s, const uint8_t* rgba, int width, int height) {
 }
 
 int pt_texture_create_rgba8(pt_scene* s, const uint8_t* rgba, int width, int height, uint64_t* handle) {
+    PT_ON_SCENE_DEVICE(s);
     if (!s || !handle) return fail(PT_ERR_INVALID, "null argument");
     Texture t;
     int rc = create_texture(rgba, width, height, (size_t)width * 4, t, s->stream);
@@ -935,6 +968,7 @@ int pt_texture_create_rgba8(pt_scene* s, const uint8_t* rgba, int width, int hei
     return PT_OK;
 }
 int pt_texture_destroy(pt_scene* s, uint64_t handle) {
+    PT_ON_SCENE_DEVICE(s);
     if (!s) return fail(PT_ERR_INVALID, "null scene");
     auto it = s->textures.find(handle);
     if (it == s->textures.end()) return fail(PT_ERR_INVALID, "unknown texture");
@@ -945,18 +979,22 @@ int pt_texture_destroy(pt_scene* s, uint64_t handle) {
 }
 
 int pt_build(pt_scene* s) {
+    PT_ON_SCENE_DEVICE(s);
     if (!s) return fail(PT_ERR_INVALID, "null scene");
     return upload_and_build(s);
 }
 
 int pt_render_frame_async(pt_scene* s, const pt_camera* cam, int spp, int max_depth, uint64_t seed, uint32_t first_sample) {
+    PT_ON_SCENE_DEVICE(s);
     return render_async(s, cam, spp, max_depth, seed, first_sample);
 }
 int pt_synchronize(pt_scene* s) {
+    PT_ON_SCENE_DEVICE(s);
     if (!s) return fail(PT_ERR_INVALID, "null scene");
     return finish_frame(s, 0);
 }
 int pt_render_frame(pt_scene* s, const pt_camera* cam, int spp, int max_depth, uint64_t seed, uint32_t first_sample) {
+    PT_ON_SCENE_DEVICE(s);
     int rc = render_async(s, cam, spp, max_depth, seed, first_sample);
     if (rc) return rc;
     rc = finish_frame(s, max_depth);
@@ -964,13 +1002,21 @@ int pt_render_frame(pt_scene* s, const pt_camera* cam, int spp, int max_depth, u
     return PT_OK;
 }
 
+int pt_ensure_frame(pt_scene* s, int width, int height) {
+    PT_ON_SCENE_DEVICE(s);
+    if (!s) return fail(PT_ERR_INVALID, "null scene");
+    return ensure_frame(s, width, height);
+}
+
 int pt_reset_accum(pt_scene* s) {
+    PT_ON_SCENE_DEVICE(s);
     if (!s) return fail(PT_ERR_INVALID, "null scene");
     if (s->accum.p) CK(cudaMemsetAsync(s->accum.p, 0, (size_t)s->width * s->height * sizeof(float4), s->stream));
     return PT_OK;
 }
 
 int pt_read_accum(pt_scene* s, float* rgba, size_t nfloats) {
+    PT_ON_SCENE_DEVICE(s);
     if (!s || !rgba) return fail(PT_ERR_INVALID, "null argument");
     const size_t npix = (size_t)s->width * s->height;
     if (npix == 0 || nfloats != 4 * npix) return fail(PT_ERR_INVALID, "nfloats must be 4*width*height of the last frame");
@@ -996,6 +1042,7 @@ int pt_get_stats(pt_scene* s, pt_stats* out) {
 }
 
 int pt_trace_rays(pt_scene* s, int n, const float* rays8, int32_t* prim, float* t, float* normal3, float* hitpos3) {
+    PT_ON_SCENE_DEVICE(s);
     if (!s || !rays8 || n < 0) return fail(PT_ERR_INVALID, "bad argument");
     if (!s->built || s->dirty) return fail(PT_ERR_NOT_BUILT, "pt_build must be called after the scene changed");
     if (n == 0) return PT_OK;
@@ -1037,15 +1084,18 @@ int pt_trace_rays(pt_scene* s, int n, const float* rays8, int32_t* prim, float* 
 }
 
 int pt_last_trace_steps(pt_scene* s, int n, uint32_t* steps) {
+    PT_ON_SCENE_DEVICE(s);
     if (!s || !steps || n <= 0) return fail(PT_ERR_INVALID, "bad argument");
     if (!s->opt_count_steps || s->scratch_i[1].n < (size_t)n) return fail(PT_ERR_INVALID, "needs PT_OPT_COUNT_STEPS and a previous pt_trace_rays of >= n rays");
-    CK(cudaMemcpy(steps, s->scratch_i[1].p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpyAsync(steps, s->scratch_i[1].p, (size_t)n * 4, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
     return PT_OK;
 }
 
 int pt_shade_batch(pt_scene* s, int n, const pt_material* mats, int n_mats, const int32_t* mat_idx, const float* pos3,
                    const float* normal3, const float* in_dir3, const float* u3, float* bounce3, float* atten3,
                    float* radiance3, int32_t* n_draws) {
+    PT_ON_SCENE_DEVICE(s);
     (void)pos3;
     if (!s || !mats || !mat_idx || !normal3 || !in_dir3 || !u3 || n < 0 || n_mats <= 0) return fail(PT_ERR_INVALID, "bad argument");
     if (n == 0) return PT_OK;
@@ -1080,6 +1130,7 @@ int pt_shade_batch(pt_scene* s, int n, const pt_material* mats, int n_mats, cons
 }
 
 int pt_raygen_batch(pt_scene* s, const pt_camera* cam, int n, const int32_t* xy, const float* u3, float* rays8) {
+    PT_ON_SCENE_DEVICE(s);
     if (!s || !cam || !xy || !u3 || !rays8 || n < 0) return fail(PT_ERR_INVALID, "bad argument");
     if (n == 0) return PT_OK;
     cudaStream_t st = s->stream;
@@ -1095,6 +1146,7 @@ int pt_raygen_batch(pt_scene* s, const pt_camera* cam, int n, const int32_t* xy,
 }
 
 int pt_sky_lookup(pt_scene* s, int n, const float* dir3, float* rgb3) {
+    PT_ON_SCENE_DEVICE(s);
     if (!s || !dir3 || !rgb3 || n < 0) return fail(PT_ERR_INVALID, "bad argument");
     if (n == 0) return PT_OK;
     int rc = ensure_sky(s); if (rc) return rc;
@@ -1110,6 +1162,7 @@ int pt_sky_lookup(pt_scene* s, int n, const float* dir3, float* rgb3) {
 }
 
 int pt_philox_uniforms(pt_scene* s, int n, uint64_t seed, const uint32_t* pss, float* u4) {
+    PT_ON_SCENE_DEVICE(s);
     if (!s || !pss || !u4 || n < 0) return fail(PT_ERR_INVALID, "bad argument");
     if (n == 0) return PT_OK;
     cudaStream_t st = s->stream;
@@ -1169,17 +1222,23 @@ int pt_camera_control(pt_camera* cam, int op, float arg, float move_speed) {
 
 int pt_dispatch_ray(pt_scene* s, const pt_camera* cam, int max_depth, uint64_t seed, uint32_t sample_idx,
                     uint8_t* bgra_out, size_t nbytes) {
+    PT_ON_SCENE_DEVICE(s);
     if (!bgra_out) return fail(PT_ERR_INVALID, "null argument");
     return display_dispatch(s, cam, max_depth, seed, sample_idx, bgra_out, nbytes);
 }
 
 int pt_dispatch_ray_begin(pt_scene* s, const pt_camera* cam, int max_depth, uint64_t seed, uint32_t sample_idx) {
+    PT_ON_SCENE_DEVICE(s);
     return display_begin(s, cam, max_depth, seed, sample_idx);
 }
-int pt_dispatch_ray_end(pt_scene* s, const uint8_t** bgra, size_t* nbytes) { return display_end(s, bgra, nbytes); }
+int pt_dispatch_ray_end(pt_scene* s, const uint8_t** bgra, size_t* nbytes) {
+    PT_ON_SCENE_DEVICE(s);
+    return display_end(s, bgra, nbytes);
+}
 
 int pt_dispatch_ray_frame(pt_scene* s, const pt_camera* cam, int max_depth, uint64_t seed, uint32_t sample_idx,
                           const uint8_t** bgra, size_t* nbytes) {
+    PT_ON_SCENE_DEVICE(s);
     if (!bgra) return fail(PT_ERR_INVALID, "null argument");
     int rc = display_dispatch(s, cam, max_depth, seed, sample_idx, nullptr, 0);
     if (rc) return rc;

@@ -475,7 +475,7 @@ __global__ void PT_BOUNCE_BOUNDS k_bounce(const BounceArgs a) {
 // ---- stage 3: accumulate the wave into the frame's SUM buffer, sample order, fp32 -------------------------
 // (the reference's Mix keeps a running mean of CLAMPED, denoised samples, path_tracer.cu:241-254; the
 // unclamped sum is what spp-sharding across GPUs needs -- the display pipeline is pt_dispatch_ray)
-__global__ void __launch_bounds__(256) k_accumulate(uint32_t npix, uint32_t n_samples, const float4* __restrict__ path_out,
+__global__ void __launch_bounds__(256, 4) k_accumulate(uint32_t npix, uint32_t n_samples, const float4* __restrict__ path_out,
                                                     float4* __restrict__ accum) {
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += stride) {

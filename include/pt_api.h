@@ -130,6 +130,10 @@ int pt_render_frame(pt_scene* s, const pt_camera* cam, int spp, int max_depth, u
 /* same, but only enqueues the work on the scene's stream */
 int pt_render_frame_async(pt_scene* s, const pt_camera* cam, int spp, int max_depth, uint64_t seed, uint32_t first_sample);
 int pt_synchronize(pt_scene* s);
+/* make the accumulation buffer exist (zeroed) for a width x height frame without rendering into it: a rank of a
+ * sample-sharded frame whose shard is empty still has to contribute a SUM buffer to the reduce.  A no-op when the
+ * buffer already has that size (it is NOT cleared then: pt_reset_accum does that). */
+int pt_ensure_frame(pt_scene* s, int width, int height);
 /* zero the accumulation buffer (the reference's only reset is MotionalCamera::Refresh,
  * cuSrc/motional_camera.cu:43-45 + path_tracer.cu:250) */
 int pt_reset_accum(pt_scene* s);

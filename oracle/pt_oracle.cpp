@@ -6,7 +6,7 @@
  * PARITY PIN: the reference ships no tests or golden vectors, so this file is
  * pinned against the reference's own sources compiled for the host (oracle/_ref/libpt_ref_host.so,
  * built by oracle/ref_build/Makefile) -- bit-exact on trace / shade / raygen / render in
- * tests/test_oracle_pin.py -- and against tests/golden/ (npz files) generated from that library by
+ * tests/test_oracle.py -- and against tests/golden/ (npz files) generated from that library by
  * tests/golden/make_golden.py.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` legs may

@@ -105,3 +105,59 @@ def test_pipelined_dispatch_delivers_the_same_frames_in_order(sky):
         b.dispatch_ray_end()                                             # nothing in flight
     assert len(got) == 6 and all(np.array_equal(g, w) for g, w in zip(got, want))
     a.close(); b.close()
+
+
+def test_dispatch_modes_mix_and_resize_on_one_scene(sky):
+    """One scene through frame -> begin/end -> frame -> resize -> begin/end -> frame: the scene-owned page-locked
+    frames, the copy stream and its events live until pt_scene_destroy (the reference's output_buffer_ lives as long
+    as its PathTracer, path_tracer.cu:303-304) -- round 1 tore them down inside pt_dispatch_ray_frame."""
+    sc = scenes.sphere_field(300, 256, 144)
+    small = scenes.sphere_field(300, 128, 72)
+    ref, ref_small = api.Renderer(sc, sky), api.Renderer(small, sky)
+    want = {i: ref.dispatch_ray(sc.camera, i, 8, 2).copy() for i in range(1, 7)}
+    r = api.Renderer(sc, sky)
+    assert np.array_equal(r.dispatch_ray_frame(sc.camera, 1, 8, 2), want[1])
+    r.dispatch_ray_begin(sc.camera, 2, 8, 2)
+    assert np.array_equal(r.dispatch_ray_end(), want[2])
+    assert np.array_equal(r.dispatch_ray_frame(sc.camera, 3, 8, 2), want[3])       # used to free the pipelined frames
+    r.dispatch_ray_begin(sc.camera, 4, 8, 2); r.dispatch_ray_begin(sc.camera, 5, 8, 2)
+    assert np.array_equal(r.dispatch_ray_end(), want[4]) and np.array_equal(r.dispatch_ray_end(), want[5])
+    assert np.array_equal(r.dispatch_ray(sc.camera, 6, 8, 2), want[6])
+    # resize down and up again, in every mode (sample 1 restarts the running mean at the new size)
+    w1 = ref_small.dispatch_ray(small.camera, 1, 8, 2).copy()
+    w2 = ref_small.dispatch_ray(small.camera, 2, 8, 2).copy()
+    assert np.array_equal(r.dispatch_ray_frame(small.camera, 1, 8, 2), w1)
+    r.dispatch_ray_begin(small.camera, 2, 8, 2)
+    with pytest.raises(api.PtError):                                              # frame size changed with one in flight
+        r.dispatch_ray_begin(sc.camera, 1, 8, 2)
+    assert np.array_equal(r.dispatch_ray_end(), w2)
+    r.dispatch_ray_begin(sc.camera, 1, 8, 2)
+    assert np.array_equal(r.dispatch_ray_end(), want[1])
+    assert np.array_equal(r.dispatch_ray_frame(sc.camera, 2, 8, 2), want[2])
+    for x in (r, ref, ref_small):
+        x.close()
+
+
+def test_scene_destroy_returns_all_device_and_pinned_memory(sky):
+    """50 scenes that each use both dispatch modes and a render: device memory after == before (cudaMemGetInfo),
+    i.e. pt_scene_destroy frees the display frames, the pipelined buffers and the wave queues."""
+    import torch
+    sc = scenes.sphere_field(200, 640, 360)
+
+    def one():
+        r = api.Renderer(sc, sky)
+        r.set_option(api.PT_OPT_WAVE_PATHS, 1 << 20)
+        r.dispatch_ray_frame(sc.camera, 1, 4, 1)
+        r.dispatch_ray_begin(sc.camera, 2, 4, 1); r.dispatch_ray_end()
+        r.render(sc.camera, 2, 4, seed=1); r.read_accum()
+        r.close()
+
+    one(); one()                                   # context, module and allocator warm-up
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info()
+    for _ in range(50):
+        one()
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info()
+    # one scene holds ~40 MB here; 50 leaked scenes would be 2 GB.  Allow the driver a few MB of slack.
+    assert free0 - free1 < 16 << 20, f"device memory shrank by {(free0 - free1) / 2**20:.1f} MiB over 50 scenes"
