@@ -18,6 +18,7 @@ LIB_PATH_FMA = os.path.join(_HERE, "libpt_b200_fma.so")  # nvcc-contracted arith
 
 PT_OPT_WAVE_PATHS, PT_OPT_STAGE_TIMING, PT_OPT_TIE_ORDER, PT_OPT_SKY_QUARTER_ROWS = 1, 2, 3, 4
 PT_OPT_TRAV_INNER_RUN, PT_OPT_COUNT_STEPS, PT_OPT_REF_LEAF_BOXES, PT_OPT_SAH_PASSES, PT_OPT_SAH_TREELETS = 7, 8, 9, 10, 11
+PT_OPT_ENTRY_GRID, PT_OPT_ENTRY_CELLS_PER_PRIM = 12, 13
 
 
 class PtMaterial(C.Structure):
@@ -36,7 +37,8 @@ class PtStats(C.Structure):
                 ("traverse_ms", C.c_float), ("shade_ms", C.c_float), ("build_ms", C.c_float),
                 ("bvh_nodes", C.c_uint32), ("wave_paths", C.c_uint32), ("traverse_launches", C.c_uint32),
                 ("waves", C.c_uint32), ("node_steps", C.c_uint64), ("prim_tests", C.c_uint64), ("hit_records", C.c_uint64),
-                ("bvh_sah_lbvh", C.c_float), ("bvh_sah", C.c_float)]
+                ("bvh_sah_lbvh", C.c_float), ("bvh_sah", C.c_float),
+                ("entry_levels", C.c_uint32), ("entry_cells", C.c_uint32)]
 
 
 EXPORTS = [

@@ -95,6 +95,8 @@ struct pt_scene {
     int opt_inner_run = 4;
     int opt_sah_treelets = 0;      // 1: the refit passes restructure 7-leaf treelets by dynamic programming (slower build, lower SAH)
     int opt_sah_passes = 4;        // SAH refit passes (tree rotations) after the Karras build; 0: plain LBVH
+    int opt_entry_grid = 12;       // finest level the entry grid may use (0: no grid, every walk starts at the root)
+    int opt_entry_cells_per_prim = 2;   // the finest level has at most this many blocks per primitive
     // device scene
     DevBuf<float4> geo0, geo1, nodes, leaf_mn, leaf_mx, leaf_c, inner_mn, inner_mx, test_mn, test_mx;
     DevBuf<MaterialRec> mats;
@@ -104,6 +106,9 @@ struct pt_scene {
     DevBuf<uint32_t> codes, codes_sorted, ids, ids_sorted, bounds6;
     DevBuf<int> orig_id;
     DevBuf<unsigned char> cub_tmp;
+    DevBuf<int4> grid_cells;
+    DevBuf<uint4> grid_levels;
+    EntryGrid grid{nullptr, nullptr, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, 0, -1};
     int n_plat = 0, n_tree = 0, has_emitters = 0;
     Texture sky;
     std::map<uint64_t, Texture> textures;
@@ -299,6 +304,63 @@ struct RefOrder {
     }
 };
 
+// Sizes, uploads and fills the entry grid (struct EntryGrid) for the tree that was just packed.  The gridded box is
+// computed on the host from the primitives (no device round trip): it only has to CONTAIN every leaf box, so it is
+// padded by 2^-10 of the scene's size plus the boxes' own inflation.
+int build_entry_grid(pt_scene* s, const std::vector<int>& tree_prims) {
+    s->grid.lmax = -1;
+    const int nt = (int)tree_prims.size();
+    if (s->opt_entry_grid <= 0 || s->opt_ref_leaf_boxes || nt < 2) return PT_OK;
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, amax = 0.0;
+    // tree_prims holds DEVICE indices; the host primitives are found through the same rank table the upload used,
+    // so walk the host list and skip platforms instead
+    for (const HostPrim& p : s->prims) {
+        if (p.type != PT_PRIM_SPHERE && p.type != PT_PRIM_CYLINDER) continue;
+        const double ar = std::fabs((double)p.radius);
+        const double hy = p.type == PT_PRIM_CYLINDER ? std::fabs((double)p.height) / 2 + 1e-4 : ar;
+        const double e[3] = {ar, hy, ar};
+        for (int k = 0; k < 3; ++k) {
+            lo[k] = std::min(lo[k], (double)p.c[k] - e[k]); hi[k] = std::max(hi[k], (double)p.c[k] + e[k]);
+            amax = std::max(amax, std::fabs((double)p.c[k]) + e[k]);
+        }
+    }
+    double size = std::max(std::max(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
+    if (!(size > 0.0) || !(size < 1e30) || !(amax < 1e30)) return PT_OK;      // degenerate or non-finite scene: no grid
+    const double pad = size / 1024.0 + amax * 2e-6 + 1e-6;
+    for (int k = 0; k < 3; ++k) { lo[k] -= pad; hi[k] += pad; }
+    size += 2 * pad;
+    int kexp = 0;
+    (void)std::frexp(size, &kexp);                 // size = m 2^kexp, 0.5 <= m < 1  =>  2^kexp > size
+    if (kexp < -100 || kexp > 100) return PT_OK;
+    std::vector<uint4> levels;
+    uint64_t total = 0;
+    const uint64_t cap_level = (uint64_t)s->opt_entry_cells_per_prim * (uint64_t)nt + 64, cap_total = 4u << 20;
+    for (int l = 0; l <= s->opt_entry_grid && l <= 20; ++l) {
+        const double cell = std::ldexp(1.0, kexp - l);
+        uint64_t n[3];
+        for (int k = 0; k < 3; ++k) n[k] = (uint64_t)std::max(1.0, std::ceil((hi[k] - lo[k]) / cell));
+        const uint64_t cells = n[0] * n[1] * n[2];
+        if (l > 0 && (cells > cap_level || total + cells > cap_total)) break;
+        levels.push_back(make_uint4((uint32_t)total, (uint32_t)n[0], (uint32_t)n[1], (uint32_t)n[2]));
+        total += cells;
+    }
+    const int lmax = (int)levels.size() - 1;
+    if (lmax < 1) return PT_OK;
+    CK(s->grid_levels.reserve(levels.size())); CK(s->grid_cells.reserve(total));
+    CK(cudaMemcpyAsync(s->grid_levels.p, levels.data(), levels.size() * sizeof(uint4), cudaMemcpyHostToDevice, s->stream));
+    EntryGridBuild b;
+    b.cells = s->grid_cells.p; b.levels = s->grid_levels.p; b.org = make_float3((float)lo[0], (float)lo[1], (float)lo[2]);
+    b.k = kexp; b.lmax = lmax; b.n_cells = (uint32_t)total;
+    k_entry_grid<<<(unsigned)((total + 127) / 128), 128, 0, s->stream>>>(b, s->nodes.p);
+    s->stats.launches += 1;
+    s->grid.cells = s->grid_cells.p; s->grid.levels = s->grid_levels.p; s->grid.org = b.org;
+    // (float) conversions round to nearest: the padding is three orders of magnitude above that
+    s->grid.hi = make_float3((float)hi[0], (float)hi[1], (float)hi[2]);
+    s->grid.k = kexp; s->grid.lmax = lmax;
+    s->stats.entry_levels = (uint32_t)lmax; s->stats.entry_cells = (uint32_t)total;
+    return PT_OK;
+}
+
 int upload_and_build(pt_scene* s) {
     const int n = (int)s->prims.size();
     cudaStream_t st = s->stream;
@@ -360,6 +422,8 @@ int upload_and_build(pt_scene* s) {
     }
     s->n_plat = (int)py.size();
     s->n_tree = (int)tree.size();
+    s->grid.lmax = -1; s->grid.cells = nullptr; s->grid.levels = nullptr;
+    s->stats.entry_levels = 0; s->stats.entry_cells = 0;
     const int nt = s->n_tree;
     cudaEvent_t eb0, eb1;
     CK(cudaEventCreate(&eb0)); CK(cudaEventCreate(&eb1));
@@ -389,14 +453,14 @@ int upload_and_build(pt_scene* s) {
             CK(cub::DeviceRadixSort::SortPairs(s->cub_tmp.p, tmp_bytes, s->codes.p, s->codes_sorted.p, s->ids.p, s->ids_sorted.p, nt, 0, 30, st));
             k_lbvh_hierarchy<<<gb, tb, 0, st>>>(nt, s->codes_sorted.p, s->children.p, s->parent_inner.p, s->parent_leaf.p);
             CK(s->node_height.reserve(nt));
-            LbvhTree tree;
-            tree.sorted_ids = s->ids_sorted.p; tree.leaf_mn = s->leaf_mn.p; tree.leaf_mx = s->leaf_mx.p;
-            tree.children = s->children.p; tree.parent_of_inner = s->parent_inner.p; tree.parent_of_leaf = s->parent_leaf.p;
-            tree.inner_mn = s->inner_mn.p; tree.inner_mx = s->inner_mx.p; tree.height = s->node_height.p;
+            LbvhTree lt;
+            lt.sorted_ids = s->ids_sorted.p; lt.leaf_mn = s->leaf_mn.p; lt.leaf_mx = s->leaf_mx.p;
+            lt.children = s->children.p; lt.parent_of_inner = s->parent_inner.p; lt.parent_of_leaf = s->parent_leaf.p;
+            lt.inner_mn = s->inner_mn.p; lt.inner_mx = s->inner_mx.p; lt.height = s->node_height.p;
             // pass 0 fits the boxes of the Karras tree; every further pass is a SAH refit (tree rotations + fit)
             for (int pass = 0; pass <= s->opt_sah_passes; ++pass) {
                 if (pass > 0) CK(cudaMemsetAsync(s->flags.p, 0, nt * sizeof(int), st));
-                k_lbvh_fit<<<gb, tb, 0, st>>>(nt, tree, s->flags.p, pass > 0 ? (s->opt_sah_treelets ? 2 : 1) : 0);
+                k_lbvh_fit<<<gb, tb, 0, st>>>(nt, lt, s->flags.p, pass > 0 ? (s->opt_sah_treelets ? 2 : 1) : 0);
                 if (pass == 0 || pass == s->opt_sah_passes) {
                     CK(s->sah_dev.reserve(2));
                     if (pass == 0) CK(cudaMemsetAsync(s->sah_dev.p, 0, 2 * sizeof(float), st));
@@ -408,6 +472,8 @@ int upload_and_build(pt_scene* s) {
             k_lbvh_pack<<<gb, tb, 0, st>>>(nt, s->ids_sorted.p, s->bvh_prims.p, s->geo1.p, s->leaf_mn.p, s->leaf_mx.p,
                                            s->children.p, s->inner_mn.p, s->inner_mx.p, s->nodes.p);
             s->stats.launches += 5 + 2;   // + the radix sort's own kernels (library), counted as 2
+            int rc = build_entry_grid(s, tree);
+            if (rc) return rc;
         }
         CK(cudaGetLastError());
     }
@@ -424,6 +490,7 @@ int upload_and_build(pt_scene* s) {
 
 SceneDev scene_dev(pt_scene* s) {
     SceneDev d;
+    d.grid = s->grid;
     d.nodes = s->nodes.p; d.geo0 = s->geo0.p; d.geo1 = s->geo1.p; d.mats = s->mats.p;
     d.plat_y = s->plat_y.p; d.plat_id = s->plat_id.p; d.orig_id = s->orig_id.p;
     d.n_plat = s->n_plat; d.n_tree_prims = s->n_tree; d.sky = s->sky.obj; d.has_emitters = s->has_emitters;
@@ -490,15 +557,15 @@ HitQueues hit_queues(pt_scene* s, int k) {
 int launch_config(pt_scene* s) {
     if (s->grid_bounce) return PT_OK;
     int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bounce<SRC_HITS, false>, 32 * PT_BOUNCE_WARPS, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bounce<SRC_HITS, false>, 32 * PT_BOUNCE_WARPS, PT_BOUNCE_SMEM));
     s->grid_bounce = s->sm_count * std::max(occ, 1);
     return PT_OK;
 }
 
 template <int SRC>
 void launch_bounce(pt_scene* s, const BounceArgs& a, cudaStream_t st) {
-    if (s->opt_count_steps) k_bounce<SRC, true><<<s->grid_bounce, 32 * PT_BOUNCE_WARPS, 0, st>>>(a);
-    else k_bounce<SRC, false><<<s->grid_bounce, 32 * PT_BOUNCE_WARPS, 0, st>>>(a);
+    if (s->opt_count_steps) k_bounce<SRC, true><<<s->grid_bounce, 32 * PT_BOUNCE_WARPS, PT_BOUNCE_SMEM, st>>>(a);
+    else k_bounce<SRC, false><<<s->grid_bounce, 32 * PT_BOUNCE_WARPS, PT_BOUNCE_SMEM, st>>>(a);
 }
 
 int render_async(pt_scene* s, const pt_camera* cam, int spp, int max_depth, uint64_t seed, uint32_t first_sample,
@@ -868,7 +935,7 @@ void pt_scene_destroy(pt_scene* s) {
     s->codes.release(); s->codes_sorted.release(); s->ids.release(); s->ids_sorted.release(); s->bounds6.release();
     s->orig_id.release(); s->cub_tmp.release(); s->accum.release(); s->read_tmp.release(); s->path_out.release(); s->hit.release();
     s->ctrl.release(); s->q_o.release(); s->q_d.release(); s->seg_counter.release();
-    s->node_height.release(); s->sah_dev.release();
+    s->node_height.release(); s->sah_dev.release(); s->grid_cells.release(); s->grid_levels.release();
     for (int k = 0; k < 2; ++k) { s->hq_o[k].release(); s->hq_d[k].release(); s->hq_thr[k].release(); s->hq_hit[k].release(); s->scratch_i[k].release(); }
     for (auto& b : s->scratch_f) b.release();
     s->disp_color.release(); s->disp_normal.release(); s->disp_mix.release(); s->disp_depth.release(); s->disp_bgra.release();
@@ -896,6 +963,12 @@ int pt_set_option(pt_scene* s, int option, int64_t value) {
         case PT_OPT_SAH_PASSES:
             if (value < 0 || value > 16) return fail(PT_ERR_INVALID, "PT_OPT_SAH_PASSES: 0 .. 16");
             s->opt_sah_passes = (int)value; s->dirty = true; return PT_OK;
+        case PT_OPT_ENTRY_GRID:
+            if (value < 0 || value > 20) return fail(PT_ERR_INVALID, "PT_OPT_ENTRY_GRID: 0 (off) .. 20 levels");
+            s->opt_entry_grid = (int)value; s->dirty = true; return PT_OK;
+        case PT_OPT_ENTRY_CELLS_PER_PRIM:
+            if (value < 1 || value > 64) return fail(PT_ERR_INVALID, "PT_OPT_ENTRY_CELLS_PER_PRIM: 1 .. 64");
+            s->opt_entry_cells_per_prim = (int)value; s->dirty = true; return PT_OK;
         case PT_OPT_TRAV_INNER_RUN:
             if (value < 1 || value > 1024) return fail(PT_ERR_INVALID, "inner_run must be 1..1024");
             s->opt_inner_run = (int)value; return PT_OK;
@@ -1067,9 +1140,9 @@ int pt_trace_rays(pt_scene* s, int n, const float* rays8, int32_t* prim, float* 
         CK(s->scratch_i[1].reserve(n));
         CK(cudaMemsetAsync(s->seg_counter.p, 0, 4 * sizeof(unsigned long long), st));
         args.ray_steps = (uint32_t*)s->scratch_i[1].p;
-        k_bounce<SRC_RAYS, true><<<s->grid_bounce, 32 * PT_BOUNCE_WARPS, 0, st>>>(args);
+        k_bounce<SRC_RAYS, true><<<s->grid_bounce, 32 * PT_BOUNCE_WARPS, PT_BOUNCE_SMEM, st>>>(args);
     } else {
-        k_bounce<SRC_RAYS, false><<<s->grid_bounce, 32 * PT_BOUNCE_WARPS, 0, st>>>(args);
+        k_bounce<SRC_RAYS, false><<<s->grid_bounce, 32 * PT_BOUNCE_WARPS, PT_BOUNCE_SMEM, st>>>(args);
     }
     k_unpack_hits<<<g, 256, 0, st>>>(n, scene_dev(s), s->q_o.p, s->q_d.p, s->hit.p, s->scratch_i[0].p,
                                      s->scratch_f[2].p, s->scratch_f[3].p, s->scratch_f[4].p);

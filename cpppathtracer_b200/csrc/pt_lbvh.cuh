@@ -458,6 +458,65 @@ __global__ void k_lbvh_pack(int n, const uint32_t* __restrict__ sorted_ids, cons
     nodes[4 * i + 3] = make_float4(__int_as_float(c0), __int_as_float(c1), 0.f, 0.f);
 }
 
+// pass 6: the entry grid (struct EntryGrid, pt_wavefront.cuh).  One thread per block of one level: the tree is pruned
+// by the block's box -- a node is replaced by those of its children whose boxes overlap the block, as long as the
+// frontier stays within four links.  A node with ONE overlapping child is always replaced (that is the descent a ray
+// would otherwise walk); a node with two is split when there is room (a block that straddles a high split plane of
+// the tree then gets the deep nodes on both sides instead of their far-away common ancestor).  Conservative by
+// construction: a primitive whose leaf box overlaps the block is below one of the frontier's links, because all of its
+// ancestors' boxes overlap the block too.  Links: >= 0 inner node, < 0 leaf (as in the nodes), 0x7fffffff none.
+struct EntryGridBuild {
+    int4* cells;
+    const uint4* levels;     // (first cell, nx, ny, nz)
+    float3 org;
+    int k, lmax;
+    uint32_t n_cells;
+};
+__device__ __forceinline__ bool box_overlaps_block(float cx, float cy, float cz, float hx, float hy, float hz, float3 bc, float bh) {
+    return fabsf(cx - bc.x) <= hx + bh && fabsf(cy - bc.y) <= hy + bh && fabsf(cz - bc.z) <= hz + bh;
+}
+__global__ void k_entry_grid(EntryGridBuild g, const float4* __restrict__ nodes) {
+    const uint32_t cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= g.n_cells) return;
+    int l = 0;
+    while (l < g.lmax && cell >= g.levels[l + 1].x) ++l;
+    const uint4 lv = g.levels[l];
+    uint32_t rem = cell - lv.x;
+    const uint32_t iz = rem % lv.w; rem /= lv.w;
+    const uint32_t iy = rem % lv.z; const uint32_t ix = rem / lv.z;
+    const float s = __int_as_float((g.k - l + 127) << 23);              // cell size 2^(k-l)
+    // the block spans two cells per axis; its half-extent is padded by 2^-18 of itself against the rounding of the
+    // ray side's (mn - org) * 2^(l-k) <= i + 2 test
+    const float3 bc = f3(g.org.x + ((float)ix + 1.f) * s, g.org.y + ((float)iy + 1.f) * s, g.org.z + ((float)iz + 1.f) * s);
+    const float bh = s * 1.000004f + 4e-7f * fmaxf(fmaxf(fabsf(bc.x), fabsf(bc.y)), fabsf(bc.z));
+    int f[4] = {0, 0x7fffffff, 0x7fffffff, 0x7fffffff};
+    int n = 1;
+    uint32_t closed = 0u;                                               // links that must not be expanded any further
+    for (int iter = 0; iter < 4096; ++iter) {
+        int j = -1;
+#pragma unroll
+        for (int q = 3; q >= 0; --q) if (q < n && f[q] >= 0 && !((closed >> q) & 1u)) j = q;
+        if (j < 0) break;
+        const float4* p = nodes + 4 * (size_t)f[j];
+        const float4 n0 = p[0], n1 = p[1], n2 = p[2], n3 = p[3];
+        const bool ha = box_overlaps_block(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, bc, bh);
+        const bool hb = box_overlaps_block(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, bc, bh);
+        const int add = (int)ha + (int)hb;
+        if (n - 1 + add > 4) { closed |= 1u << j; continue; }
+        // remove link j (the order of the others is kept, and with it their `closed` bits), append the children
+        const uint32_t low = closed & ((1u << j) - 1u), high = (closed >> (j + 1)) << j;
+        closed = low | high;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) if (q >= j) f[q] = f[q + 1];
+        --n;
+        if (ha) { f[n] = __float_as_int(n3.x); ++n; }
+        if (hb) { f[n] = __float_as_int(n3.y); ++n; }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) if (q >= n) f[q] = 0x7fffffff;
+    }
+    g.cells[cell] = make_int4(f[0], f[1], f[2], f[3]);
+}
+
 // a tree over a single primitive: one node whose second child can never be entered
 __global__ void k_lbvh_single(const int* __restrict__ bvh_prims, const float4* __restrict__ geo0,
                               const float4* __restrict__ geo1, float4* __restrict__ nodes) {

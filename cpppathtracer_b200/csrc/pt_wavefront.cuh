@@ -18,7 +18,7 @@
 namespace pt {
 
 #define PT_MISS_CODE 0xFFFFFFFFu
-#define PT_STACK 64
+#define PT_STACK 68   // Karras trees over 30-bit codes + index tie-break are <= 62 deep, + the sentinel, + 3 entry-grid links
 #define PT_FULL 0xffffffffu
 // build-time switches of k_bounce (tools/build_variants.sh times the alternatives on one box)
 #ifndef PT_RCP_APPROX
@@ -32,6 +32,9 @@ namespace pt {
 #endif
 #ifndef PT_STACK_TOP
 #define PT_STACK_TOP 1
+#endif
+#ifndef PT_BOUNCE_WARPS
+#define PT_BOUNCE_WARPS 4
 #endif
 
 // One control block per bounce, zeroed once per wave.  Every counter that takes atomics sits on its own
@@ -50,7 +53,22 @@ static_assert(sizeof(BounceCtrl) == 128 * (4 + NUM_BINS), "one line per counter"
 
 // Primitives live on the device in the reference's leaf VISITING order (or insertion order when
 // PT_OPT_TIE_ORDER is off): "device index" below always means that position.
+// Entry grid (pt_lbvh.cuh, k_entry_grid): where the walk of a SHORT ray starts.  A ray that is clipped to the scene's box
+// and to its platform hit is a segment; every level l of the grid tiles the box with overlapping blocks of 2 x 2 x 2
+// cubic cells of size 2^(k-l), and each block stores the frontier (<= 4 links) of the tree pruned by the block's box
+// with every single-child descent followed.  A segment whose bounding box has extent < cell size fits in one block,
+// so its walk starts at that frontier instead of the root: the root-to-neighbourhood descent (log2 N dependent node
+// visits that mostly find one child) is paid once per block at build time instead of once per ray.
+struct EntryGrid {
+    const int4* cells;        // all levels, level l at levels[l].x
+    const uint4* levels;      // (first cell, nx, ny, nz) per level; level 0 is one block = the root
+    float3 org, hi;           // the gridded box: contains every leaf box, padded
+    int k;                    // cell size of level l is 2^(k - l)
+    int lmax;                 // finest level; < 0: no grid (walks start at the root)
+};
+
 struct SceneDev {
+    EntryGrid grid;
     const float4* nodes;      // LBVH, 4 x float4 per inner node
     const float4* geo0;       // (cx, cy, cz, radius)
     const float4* geo1;       // (height, y_pos, bits type, bits (bin<<28 | material slot))
@@ -77,9 +95,8 @@ struct SceneDev {
 #ifndef PT_BOUNCE_MIN_BLOCKS
 #define PT_BOUNCE_MIN_BLOCKS 0   // 0: let ptxas choose (56 registers, 9 CTAs/SM). Same-box A/B: forcing 10 CTAs (48 regs) is 3 % slower on C2
 #endif
-#ifndef PT_BOUNCE_WARPS
-#define PT_BOUNCE_WARPS 4
-#endif
+
+#define PT_BOUNCE_SMEM ((size_t)PT_STACK_SMEM * 32 * PT_BOUNCE_WARPS * sizeof(int))   // dynamic shared memory per CTA
 
 struct LaneRay {
     float3 o, d;
@@ -117,6 +134,43 @@ __device__ __forceinline__ float cull_rcp(float x) {
 #endif
 }
 
+// The walk's stack.  Default: thread-local memory (L1-resident; the top entry lives in a register, PT_STACK_TOP).
+// PT_STACK_SMEM = N > 0 (build variant, A/B in profiles/): the first N entries of every thread live in shared memory,
+// laid out [entry][thread] so that a warp's accesses are conflict-free whatever the lanes' depths are (thread-local
+// memory interleaves by lane too, but lanes at different depths touch different 128-byte lines: one L1 wavefront per
+// distinct depth); deeper entries overflow to local memory.
+#ifndef PT_STACK_SMEM
+#define PT_STACK_SMEM 0
+#endif
+#if PT_STACK_SMEM > 0
+__device__ __forceinline__ void stack_store(int* stack, int sp, int v) {
+    extern __shared__ int pt_smem_stack[];
+    if (sp < PT_STACK_SMEM) pt_smem_stack[sp * (32 * PT_BOUNCE_WARPS) + threadIdx.x] = v;
+    else stack[sp - PT_STACK_SMEM] = v;
+}
+__device__ __forceinline__ int stack_load(const int* stack, int sp) {
+    extern __shared__ int pt_smem_stack[];
+    return sp < PT_STACK_SMEM ? pt_smem_stack[sp * (32 * PT_BOUNCE_WARPS) + threadIdx.x] : stack[sp - PT_STACK_SMEM];
+}
+#else
+__device__ __forceinline__ void stack_store(int* stack, int sp, int v) { stack[sp] = v; }
+__device__ __forceinline__ int stack_load(const int* stack, int sp) { return stack[sp]; }
+#endif
+__device__ __forceinline__ void stack_push(LaneRay& r, int* stack, int x) {
+#if PT_STACK_TOP
+    stack_store(stack, r.sp++, r.top); r.top = x;
+#else
+    stack_store(stack, r.sp++, x);
+#endif
+}
+__device__ __forceinline__ int stack_pop(LaneRay& r, int* stack) {
+#if PT_STACK_TOP
+    const int x = r.top; r.top = stack_load(stack, --r.sp); return x;    // sp >= 1 here: entry 0 is the sentinel written by lane_setup
+#else
+    return stack_load(stack, --r.sp);
+#endif
+}
+
 // platforms are kept out of the tree: tested first, they also give the walk its first tmax
 __device__ __forceinline__ void lane_platforms(const SceneDev& sc, float3 o, float3 d, float tmin, float& best_t, uint32_t& best_code) {
     best_code = PT_MISS_CODE;
@@ -139,30 +193,57 @@ __device__ __forceinline__ void lane_setup(const SceneDev& sc, LaneRay& r, int* 
     r.lo = r.tmin - r.slack;
     r.hi = r.best_t * 1.0000005f + r.slack;
     r.sp = 0;
-    stack[r.sp++] = PT_SENTINEL;
+    stack_store(stack, r.sp++, PT_SENTINEL);
 #if PT_STACK_TOP
     r.top = PT_SENTINEL;
 #endif
     r.node = sc.n_tree_prims > 0 ? 0 : PT_SENTINEL;
+    const EntryGrid& g = sc.grid;
+    if (g.lmax < 0 || sc.n_tree_prims <= 0) return;
+    // ---- the ray as a segment: clipped to the gridded box and to [lo, hi] (tmin .. platform hit), same FMA slabs and
+    //      the same slack as the node tests ----
+    const float x0 = fmaf(g.org.x, r.ix, -r.ox), x1 = fmaf(g.hi.x, r.ix, -r.ox);
+    const float y0 = fmaf(g.org.y, r.iy, -r.oy), y1 = fmaf(g.hi.y, r.iy, -r.oy);
+    const float z0 = fmaf(g.org.z, r.iz, -r.oz), z1 = fmaf(g.hi.z, r.iz, -r.oz);
+    const float t0 = fmaxf(fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fminf(z0, z1)) - r.slack, r.lo);
+    const float t1 = fminf(fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1)) + r.slack, r.hi);
+    if (!(t0 <= t1)) { r.node = PT_SENTINEL; return; }        // misses the box of everything in the tree
+    const float ax = fmaf(t0, r.d.x, r.o.x), ay = fmaf(t0, r.d.y, r.o.y), az = fmaf(t0, r.d.z, r.o.z);
+    const float bx = fmaf(t1, r.d.x, r.o.x), by = fmaf(t1, r.d.y, r.o.y), bz = fmaf(t1, r.d.z, r.o.z);
+    const float ex = 2e-7f * (fabsf(ax) + fabsf(bx)) + 1e-30f, ey = 2e-7f * (fabsf(ay) + fabsf(by)) + 1e-30f,
+                ez = 2e-7f * (fabsf(az) + fabsf(bz)) + 1e-30f;
+    // bounding box of the segment, inside the gridded box (nothing to hit outside of it)
+    const float mnx = fmaxf(fminf(ax, bx) - ex, g.org.x) - g.org.x, mny = fmaxf(fminf(ay, by) - ey, g.org.y) - g.org.y,
+                mnz = fmaxf(fminf(az, bz) - ez, g.org.z) - g.org.z;
+    const float mxx = fminf(fmaxf(ax, bx) + ex, g.hi.x) - g.org.x, mxy = fminf(fmaxf(ay, by) + ey, g.hi.y) - g.org.y,
+                mxz = fminf(fmaxf(az, bz) + ez, g.hi.z) - g.org.z;
+    const float ext = fmaxf(fmaxf(mxx - mnx, mxy - mny), fmaxf(mxz - mnz, 0.f));
+    // finest level whose cell size 2^(k-l) exceeds the extent: ext = m 2^x, 1 <= m < 2  =>  cell 2^(x+1), l = k - x - 1
+    int l = g.k + 126 - (__float_as_int(ext) >> 23);
+    l = l > g.lmax ? g.lmax : l;
+    if (l <= 0) return;                                        // long segment (or NaN): the root
+    const float inv_s = __int_as_float((l - g.k + 127) << 23);
+    const uint4 lv = __ldg(&g.levels[l]);
+    const float fx = mnx * inv_s, fy = mny * inv_s, fz = mnz * inv_s;
+    int ix = (int)fx, iy = (int)fy, iz = (int)fz;
+    ix = min(ix, (int)lv.y - 1); iy = min(iy, (int)lv.z - 1); iz = min(iz, (int)lv.w - 1);
+    // block (ix, iy, iz) spans cells i .. i+2 on every axis: it must contain the whole box (rounding, clamping)
+    const bool fits = fx >= (float)ix && fy >= (float)iy && fz >= (float)iz && mxx * inv_s <= (float)(ix + 2) &&
+                      mxy * inv_s <= (float)(iy + 2) && mxz * inv_s <= (float)(iz + 2);
+    if (!fits) return;
+    const int4 f = __ldg(&g.cells[lv.x + ((uint32_t)ix * lv.z + (uint32_t)iy) * lv.w + (uint32_t)iz]);
+    r.node = f.x;                                              // PT_SENTINEL: nothing overlaps the block
+    if (f.y != PT_SENTINEL) {
+        stack_push(r, stack, f.y);
+        if (f.z != PT_SENTINEL) {
+            stack_push(r, stack, f.z);
+            if (f.w != PT_SENTINEL) stack_push(r, stack, f.w);
+        }
+    }
 }
 __device__ __forceinline__ void lane_begin(const SceneDev& sc, LaneRay& r, int* stack) {
     lane_platforms(sc, r.o, r.d, r.tmin, r.best_t, r.best_code);
     lane_setup(sc, r, stack);
-}
-
-__device__ __forceinline__ void stack_push(LaneRay& r, int* stack, int x) {
-#if PT_STACK_TOP
-    stack[r.sp++] = r.top; r.top = x;
-#else
-    stack[r.sp++] = x;
-#endif
-}
-__device__ __forceinline__ int stack_pop(LaneRay& r, int* stack) {
-#if PT_STACK_TOP
-    const int x = r.top; r.top = stack[--r.sp]; return x;    // sp >= 1 here: entry 0 is the sentinel written by lane_begin
-#else
-    return stack[--r.sp];
-#endif
 }
 
 // One 64-byte node = two 256-bit loads (LDG.E.256, new on sm_100): half the LSU instructions and L1 wavefronts

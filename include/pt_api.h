@@ -76,6 +76,8 @@ typedef struct pt_stats {
     uint64_t hit_records;     /* 56-byte hit records that went through the hit queues (segments that hit) */
     float    bvh_sah_lbvh;    /* SAH cost (sum of inner-node areas / root area) of the Karras tree ...        */
     float    bvh_sah;         /* ... and after the SAH refit passes (PT_OPT_SAH_PASSES)                        */
+    uint32_t entry_levels;    /* finest level of the entry grid built by the last pt_build (0: none)          */
+    uint32_t entry_cells;     /* blocks of the entry grid, all levels (16 bytes each)                          */
 } pt_stats;
 
 enum {
@@ -92,6 +94,11 @@ enum {
     PT_OPT_COUNT_STEPS = 8,     /* 1: use the instrumented traversal kernel that counts node visits / primitive tests */
     PT_OPT_TRAV_INNER_RUN = 7,  /* tuning: inner-node steps a lane may take before the warp regroups for leaf tests */
     PT_OPT_SAH_PASSES = 10,     /* SAH refit passes (tree rotations) after the LBVH build; default 4, 0 = plain LBVH */
+    PT_OPT_ENTRY_GRID = 12,     /* finest level of the ENTRY GRID (default 12; 0: off, every walk starts at the root).  Level l
+                                   tiles the scene's box with overlapping 2x2x2 blocks of cubic cells of 2^-l of its size; a
+                                   block stores the <= 4 tree links a ray segment inside it has to start from, so short rays
+                                   skip the root-to-neighbourhood descent.  Results do not depend on it. */
+    PT_OPT_ENTRY_CELLS_PER_PRIM = 13, /* the finest level has at most this many blocks per primitive (default 2) */
     PT_OPT_SAH_TREELETS = 11    /* 1: the refit passes restructure 7-leaf treelets by dynamic programming instead of
                                    single rotations: lower SAH (C2 11.06 vs 11.24), but 1.5 ms instead of 0.06 ms per
                                    pass at 1 k primitives -- for scenes that are built once; default 0 */
