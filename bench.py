@@ -10,10 +10,16 @@ A step = one frame of the workload (W*H*spp paths) through the wavefront path.  
 (scene upload + LBVH build + render + read-back of the mean image into pinned host memory) by wall clock.
 N > 1 is weak scaling by samples-per-pixel: every rank renders its own 64-sample Philox range of the same
 frame and the SUM buffers are reduced to rank 0 with one NCCL reduce per frame (inside the timed region).
+
+Beside the headline the line carries a `configs` block with the other BASELINE.json configurations, measured in
+the same process: C1 and C3 on one GPU (rank 0), C4 (3840x2160, a FIXED 1024 spp split over the ranks: strong
+scaling, one reduce) and C5 (120 frames round-robin over the ranks, per-frame rebuild, wall clock) on all ranks,
+and for N > 1 `multi_gpu_check`: the reduced SUM buffer against rank 0 rendering the same samples alone.
 """
 from __future__ import annotations
 
 import argparse
+import copy
 import json
 import os
 import subprocess
@@ -30,14 +36,16 @@ METRIC = "Mpaths/s at 1080p, max depth 8"
 WORKLOAD = {"workload": "C2: floor + 1000 mixed-material spheres, 1920x1080, 64 spp, depth 8",
             "width": 1920, "height": 1080, "spp": 64, "max_depth": 8, "n_spheres": 1000, "scene_seed": 12345,
             "l2": "hit queues (about 30 GB streamed per 64-spp frame, written by one launch and read by the next) exceed the 126 MB L2; no explicit flush"}
-# Algorithmic HBM bytes of the dominant kernel k_bounce: every path segment THAT HITS costs one
-# 56-byte hit record written by the launch that traces it and read by the launch that shades it (rays never leave
-# registers; a segment that leaves the scene is shaded by the sky where it ends), every path one 16-byte radiance
-# write.  SURVEY.md 8(d) budgets 144 B/segment + 16 B/path for a
-# wavefront design that also keeps rays in HBM; that figure is reported beside this one.
-ALG_BYTES_PER_SEGMENT = 112
-ALG_BYTES_PER_PATH = 16
+# HBM byte models of the dominant kernel k_bounce.
+#   a wavefront design that keeps rays in HBM moves 144 B per path segment + 16 B per path.  That is the
+#     contract's algorithmic figure and what `roofline.frac` is computed from.
+#   This kernel's own traffic: rays never leave registers, a segment that leaves the scene is shaded where it ends, so
+#     only a segment THAT HITS costs one 56-byte hit record written by the launch that traces it and read by the launch
+#     that shades it (112 B), plus 16 B of radiance per path.  Reported as `roofline_own_bytes`; ncu's measured DRAM
+#     bytes agree with this model to 4 %.
 SURVEY_BYTES_PER_SEGMENT = 144
+OWN_BYTES_PER_HIT_RECORD = 112
+BYTES_PER_PATH = 16
 
 
 def measured_peaks():
@@ -46,6 +54,15 @@ def measured_peaks():
         with open(p) as f:
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def host_threads() -> int:
+    """Host cores this process may use.  torchrun exports OMP_NUM_THREADS=1 to its workers, which made the reference
+    arm single-threaded at N > 1 in round 1: the thread count is passed to the OpenMP region explicitly instead."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 class ClockSampler:
@@ -119,17 +136,17 @@ def cpu_baseline_leg(sc, sky, budget_s: float = 15.0):
     orc = ref_host.best_oracle()
     orc.load_scene(sc)
     orc.set_sky(sky)
-    cores = orc.max_threads()
+    cores = host_threads()
     t0 = time.perf_counter()
-    _, st = orc.render(sc.camera, 1, WORKLOAD["max_depth"], seed=1)
+    _, st = orc.render(sc.camera, 1, WORKLOAD["max_depth"], seed=1, nthreads=cores)
     t1 = time.perf_counter() - t0
     spp = int(max(1, min(WORKLOAD["spp"], budget_s / max(t1, 1e-3))))
     t0 = time.perf_counter()
-    _, st = orc.render(sc.camera, spp, WORKLOAD["max_depth"], seed=1)
+    _, st = orc.render(sc.camera, spp, WORKLOAD["max_depth"], seed=1, nthreads=cores)
     dt = time.perf_counter() - t0
     return {"value": st["paths"] / dt / 1e6, "unit": "Mpaths/s", "cores": cores, "kind": orc.kind,
             "sample": f"{sc.camera.width}x{sc.camera.height} x {spp} spp of the workload scene, depth 8 "
-                      f"({st['paths'] / 1e6:.1f} M paths, {dt:.1f} s, OpenMP over rows)",
+                      f"({st['paths'] / 1e6:.1f} M paths, {dt:.1f} s, OpenMP over rows, {cores} threads)",
             "segments_per_path": st["segments"] / st["paths"]}
 
 
@@ -138,27 +155,29 @@ def reference_arm(args, out):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    cores = host_threads()
+    os.environ["OMP_NUM_THREADS"] = str(cores)     # before the OpenMP runtime of the oracle library initialises
+    os.environ.pop("OMP_THREAD_LIMIT", None)
     from oracle import ref_host
     sc, sky = build_workload()
     orc = ref_host.best_oracle()
     orc.load_scene(sc)
     orc.set_sky(sky)
-    cores = orc.max_threads()
     # bounded sample per step: ~1.5 s of CPU work
     t0 = time.perf_counter()
-    orc.render(sc.camera, 1, WORKLOAD["max_depth"], seed=1)
+    orc.render(sc.camera, 1, WORKLOAD["max_depth"], seed=1, nthreads=cores)
     t1 = time.perf_counter() - t0
     spp = int(max(1, min(WORKLOAD["spp"], 1.5 / max(t1, 1e-3))))
     for _ in range(args.warmup):
-        orc.render(sc.camera, spp, WORKLOAD["max_depth"], seed=2)
+        orc.render(sc.camera, spp, WORKLOAD["max_depth"], seed=2, nthreads=cores)
     paths = 0
     t0 = time.perf_counter()
     for k in range(args.steps):
-        _, st = orc.render(sc.camera, spp, WORKLOAD["max_depth"], seed=3, first_sample=k * spp)
+        _, st = orc.render(sc.camera, spp, WORKLOAD["max_depth"], seed=3, first_sample=k * spp, nthreads=cores)
         paths += st["paths"]
     dt = time.perf_counter() - t0
     v = paths / dt / 1e6
-    sample = f"{sc.camera.width}x{sc.camera.height} x {spp} spp per step of the workload scene, depth 8"
+    sample = f"{sc.camera.width}x{sc.camera.height} x {spp} spp per step of the workload scene, depth 8, {cores} OpenMP threads"
     print(file=out, flush=True, *[json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -168,19 +187,24 @@ def reference_arm(args, out):
         "gpu_launches": 0})])
 
 
-def fp32_view(r, cam, depth, mrays_per_s, sm_mhz):
-    """SURVEY.md 8(d)'s second ceiling: algorithmic FP32 work per segment from THIS BVH's measured visit counts
-    (instrumented kernel, 2 spp) against 148 SMs x 128 lanes x 2 flop x clock."""
+def visit_counts(r, cam, depth, spp=2):
+    """Node visits / primitive tests per segment of THIS BVH (instrumented kernel, a few spp)."""
     from cpppathtracer_b200 import api
     r.set_option(api.PT_OPT_COUNT_STEPS, 1)
     r.reset_accum()
-    r.render(cam, 2, depth, seed=7)
+    r.render(cam, spp, depth, seed=7)
     st = r.stats()
     r.set_option(api.PT_OPT_COUNT_STEPS, 0)
-    nodes, prims = st["node_steps"] / st["segments"], st["prim_tests"] / st["segments"]
+    return st["node_steps"] / st["segments"], st["prim_tests"] / st["segments"], st["paths"] / st["segments"]
+
+
+def fp32_view(r, cam, depth, mrays_per_s, sm_mhz):
+    """SURVEY.md 8(d)'s second ceiling: algorithmic FP32 work per segment from THIS BVH's measured visit counts
+    (instrumented kernel, 2 spp) against 148 SMs x 128 lanes x 2 flop x clock."""
+    nodes, prims, paths_per_seg = visit_counts(r, cam, depth)
     # per node visit two child boxes of 18 flops (slab test with precomputed 1/d), ~30 per sphere test, 10 for the
     # platform, ~150 per shade, 40 per camera ray (SURVEY.md 8d)
-    flops_seg = nodes * 2 * 18 + prims * 30 + 10 + 150 + 40 * st["paths"] / st["segments"]
+    flops_seg = nodes * 2 * 18 + prims * 30 + 10 + 150 + 40 * paths_per_seg
     peak = 148 * 128 * 2 * (sm_mhz or 1965.0) * 1e6 / 1e12
     achieved = mrays_per_s * 1e6 * flops_seg / 1e12
     return {"bound": "fp32 issue", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
@@ -220,6 +244,70 @@ def ref_cuda_leg(sc, sky):
         return {"unavailable": str(e)[:200]}
 
 
+def graze_leg(r, sc, segments=(0, 1, 2, 3)):
+    """Closest-hit primitive ids of this path against the reference's own intersection code on real path rays of the
+    config's scene (camera at 480x270, segments 0-3): north_star excludes grazing / tie rays from the bit-exact id
+    requirement and wants them COUNTED.  The oracle is the checker here, nothing it computes is timed or reported as
+    a result of the product."""
+    from oracle import ref_host
+    port = ref_host.PortOracle()
+    port.load_scene(sc)
+    ref = ref_host.RefHost() if ref_host.available() else port
+    if ref is not port:
+        ref.load_scene(sc)
+    cam = copy.deepcopy(sc.camera)
+    cam.width, cam.height = 480, 270
+    n = mism = t_diff = hits = 0
+    for seg in segments:
+        rays, valid = port.segment_rays(cam, seg, sample=0, max_depth=8, seed=1)
+        rays = rays[valid]
+        if len(rays) == 0:
+            continue
+        pg, tg, _, _ = r.trace(rays)
+        pr, tr, _, _ = ref.trace(rays)
+        bad = pg != pr
+        n += len(rays); mism += int(bad.sum())
+        both = (~bad) & (pg >= 0)
+        hits += int(both.sum()); t_diff += int((tg[both] != tr[both]).sum())
+    return {"rays": n, "prim_id_mismatches": mism, "hits_compared": hits, "hit_distance_not_bit_identical": t_diff,
+            "oracle": ref.kind, "what": "graze / tie class (DESIGN.md section 4): excluded from the bit-exact id bar and counted"}
+
+
+def config_single_gpu(name, what, sc, sky, spp, frames, depth, stream, with_graze):
+    """One BASELINE config on this rank's GPU: device-timed frames, statistics of the last one, visit counts."""
+    import torch
+    from cpppathtracer_b200 import api
+    r = api.Renderer(sc, sky)
+    r.set_stream(stream)
+    cam = sc.camera
+    for _ in range(3):
+        r.reset_accum()
+        r.render(cam, spp, depth, seed=2026, sync=False)
+    r.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(frames):
+        r.reset_accum()
+        r.render(cam, spp, depth, seed=2026, sync=False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / frames
+    r.synchronize()
+    st = r.stats()
+    nodes, prims, _ = visit_counts(r, cam, depth, spp=1 if sc.n_prims > 10000 else 2)
+    out = {"workload": what, "mpaths_per_s": cam.width * cam.height * spp / ms / 1e3, "ms_per_frame": ms, "frames_timed": frames,
+           "n_gpus": 1, "segments_per_path": st["segments"] / st["paths"], "mrays_per_s": st["segments"] / ms / 1e3,
+           "node_visits_per_segment": nodes, "prim_tests_per_segment": prims, "n_prims": sc.n_prims,
+           "bvh_sah": st["bvh_sah"], "entry_grid_levels": st["entry_levels"], "wave_paths": st["wave_paths"]}
+    if with_graze:
+        try:
+            out["graze"] = graze_leg(r, sc)
+        except Exception as e:
+            out["graze"] = {"unavailable": str(e)[:200]}
+    r.close()
+    return out
+
+
 def _quiet_stdout():
     """Libraries (NCCL's version banner) write to fd 1; the driver wants exactly ONE JSON line there.
     Point fd 1 at stderr for the duration of the run and return a file object on the real stdout."""
@@ -236,7 +324,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--no-baselines", action="store_true", help="skip the cpu / reference-CUDA baseline legs")
+    ap.add_argument("--no-baselines", action="store_true", help="skip the cpu / reference-CUDA baseline legs and the graze counts")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C1 / C3 / C4 / C5 legs (profiling runs)")
     ap.add_argument("--wave-paths", type=int, default=0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -246,7 +335,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from cpppathtracer_b200 import api, distributed as ptd
+    from cpppathtracer_b200 import api, scenes, video, distributed as ptd
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the render path has no CPU fallback")
@@ -257,12 +346,24 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     warmup = max(args.warmup, 3)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     sc, sky = build_workload()
     cam = sc.camera
     spp, depth = WORKLOAD["spp"], WORKLOAD["max_depth"]
     r = api.Renderer(sc, sky)
-    r.set_stream(torch.cuda.current_stream().cuda_stream)
+    r.set_stream(stream)
     r.set_option(api.PT_OPT_STAGE_TIMING, 1)
     if args.wave_paths:
         r.set_option(api.PT_OPT_WAVE_PATHS, args.wave_paths)
@@ -272,7 +373,7 @@ def main():
         r.reset_accum()
         r.render(cam, spp, depth, seed=2026, first_sample=first, sync=False)
         if world > 1:
-            ptd.reduce_sum_to_root(ptd.accum_tensor(r))
+            ptd.reduce_sum_to_root(ptd.accum_tensor(r), renderer=r)
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -281,9 +382,7 @@ def main():
         step()
     r.synchronize()
     launches0 = r.stats()["launches"]
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.mark_begin()
     e0.record()
@@ -299,10 +398,7 @@ def main():
     r.synchronize()
     st = r.stats()
     launches = st["launches"] - launches0
-    tms = torch.tensor([ms], device="cuda")
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms = float(tms.item())
+    ms = max_over_ranks(ms)
     paths_per_step = cam.width * cam.height * spp * world
     value = paths_per_step * args.steps / (ms * 1e-3) / 1e6
 
@@ -319,27 +415,22 @@ def main():
         r.reset_accum()
         r.render(cam, spp, depth, seed=2026, first_sample=first, sync=False)
         if world > 1:
-            ptd.reduce_sum_to_root(ptd.accum_tensor(r))
+            ptd.reduce_sum_to_root(ptd.accum_tensor(r), renderer=r)
         if rank == 0:
             r.read_accum(host_img)
         else:
             r.synchronize()
 
     e2e_step(0)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+    barrier()
     t0 = time.perf_counter()
     for k in range(e2e_steps):
         e2e_step(k)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = paths_per_step * e2e_steps / float(te.item()) / 1e6
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = paths_per_step * e2e_steps / e2e_s / 1e6
     if rank == 0:
         clocks = sampler.stop()
         if not clocks.get("samples"):
@@ -351,21 +442,45 @@ def main():
         else:
             clocks["window"] = "timed region"
 
+    # ---- N > 1: the reduced image against rank 0 rendering the same samples alone ----------------------
+    multi_check = None
+    if world > 1:
+        sc_s = scenes.sphere_field(1000, 960, 540)
+        rs = api.Renderer(sc_s, sky)
+        rs.set_stream(stream)
+        total_spp = 8 * world + 3               # not divisible by the world size on purpose
+        t = ptd.render_sharded(rs, sc_s.camera, total_spp, depth, seed=11, rank=rank, world=world)
+        if rank == 0:
+            sharded = t.cpu().numpy().reshape(540, 960, 4).copy()
+            rs.reset_accum(); rs.render(sc_s.camera, total_spp, depth, seed=11)
+            alone = ptd.accum_tensor(rs).cpu().numpy().reshape(540, 960, 4)
+            d = np.abs(sharded[..., :3] - alone[..., :3])
+            multi_check = {"what": f"960x540 x {total_spp} spp sharded over {world} ranks + one NCCL reduce, vs the same samples on rank 0 alone",
+                           "samples_ok": bool((sharded[..., 3] == total_spp).all()),
+                           "max_rel_diff": float((d / np.maximum(alone[..., :3], 1e-3)).max()),
+                           "max_abs_diff_of_sums": float(d.max()),
+                           "bitwise_equal_fraction": float((sharded[..., :3] == alone[..., :3]).mean())}
+        rs.close()
+        barrier()
+
+    line = None
     if rank == 0:
         peak, peak_src = measured_peaks()
         segs = st["segments"]                      # rays traced in the last frame on this rank
         kern_ms = st["traverse_ms"] + st["shade_ms"]   # all k_bounce launches of the last frame (CUDA events per launch)
         # k_bounce launches of the last frame: per wave `depth` launches that trace + one that only shades, which is
         # not enqueued in a scene without emitters (every launch of the timed region minus the two bookkeeping kernels
-        # per wave, per step)
+        # per wave, per step; minus nothing else: the reduce is NCCL's)
         n_launch = max(int(round(launches / max(args.steps, 1))) - 2 * st["waves"], 1)
         hits = st["hit_records"]                   # segments that hit something: the only ones with a queue record
-        alg_bytes = ALG_BYTES_PER_SEGMENT * hits + ALG_BYTES_PER_PATH * st["paths"]
-        achieved = alg_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else None
+        survey_bytes = SURVEY_BYTES_PER_SEGMENT * segs + BYTES_PER_PATH * st["paths"]
+        own_bytes = OWN_BYTES_PER_HIT_RECORD * hits + BYTES_PER_PATH * st["paths"]
+        achieved = survey_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else None
+        achieved_own = own_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else None
         # measured DRAM bytes per launch: the ncu capture is taken on a 16-spp wave (tools/profile_target.py; ncu replays
         # every launch ~40 times), the step here is one 64-spp wave of the same kernels, so the captured bytes of the
         # wave are scaled by the ratio of the wave sizes and divided by this step's launches
-        traffic = None
+        traffic, tj = None, {}
         tp = os.path.join(ROOT, "profiles", "traverse_traffic.json")
         if os.path.exists(tp):
             with open(tp) as f:
@@ -374,6 +489,7 @@ def main():
                 traffic = tj["dram_bytes_per_wave"] * (st["paths"] / tj["wave_paths"]) / n_launch
             else:
                 traffic = tj.get("dram_bytes_per_launch")
+        dram_gbs = traffic * n_launch / (kern_ms * 1e-3) / 1e9 if (traffic and kern_ms > 0) else None
         line = {
             "metric": METRIC, "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -383,25 +499,32 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "k_bounce (shade previous hits + trace the segment, fused)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                          "traffic": traffic, "peak_source": peak_src,
+                         "byte_model": "SURVEY.md 8(d): 144 B per path segment + 16 B per path (a wavefront design with ray queues in HBM)",
                          "traffic_source": "ncu --set full of a 16-spp wave (profiles/traverse_traffic.json), scaled to this step's paths, per launch",
-                         "algorithmic_bytes_per_launch": alg_bytes / n_launch, "avg_launch_ms": kern_ms / n_launch,
+                         "algorithmic_bytes_per_launch": survey_bytes / n_launch, "avg_launch_ms": kern_ms / n_launch,
                          "launches_per_step": n_launch,
                          "share_of_step": kern_ms / st["render_ms"] if st["render_ms"] > 0 else None,
-                         "hit_records_per_step": hits,
+                         "segments_per_step": segs,
+                         "dram_gbs_measured": dram_gbs, "dram_frac_measured": (dram_gbs / peak) if dram_gbs else None,
                          "note": "bound by instruction issue x SIMD efficiency (IPC 2.5-3.2 of 4, 17-30 of 32 lanes active, "
-                                 "long-scoreboard on L1/L2 node fetches; profiles/r01_v12_summary.md), not by HBM; DRAM traffic "
-                                 "equals the algorithmic bytes"},
+                                 "long-scoreboard on L1/L2 node fetches; profiles/), not by HBM: the kernel moves a quarter of "
+                                 "the bytes this model budgets (see roofline_own_bytes) because rays stay in registers"},
+            "roofline_own_bytes": {"bound": "hbm", "achieved": achieved_own, "peak": peak, "unit": "GB/s",
+                                   "frac": (achieved_own / peak) if achieved_own else None,
+                                   "byte_model": "this kernel's own traffic: 112 B per segment that hits (one 56-byte hit record written + read) + 16 B per path",
+                                   "hit_records_per_step": hits, "bytes_per_launch": own_bytes / n_launch,
+                                   "measured_over_model": (traffic * n_launch / own_bytes) if traffic else None},
             "path": {"mrays_per_s": segs / (st["render_ms"] * 1e-3) / 1e6 if st["render_ms"] > 0 else None,
                      "segments_per_path": segs / st["paths"], "render_ms_last_frame": st["render_ms"],
-                     "bounce_kernel_ms": kern_ms,
-                     "hbm_gbs_at_survey_model": (SURVEY_BYTES_PER_SEGMENT * segs + ALG_BYTES_PER_PATH * st["paths"]) / (st["render_ms"] * 1e-3) / 1e9
-                     if st["render_ms"] > 0 else None},
+                     "bounce_kernel_ms": kern_ms, "entry_grid_levels": st["entry_levels"], "entry_grid_cells": st["entry_cells"]},
             "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "what": "pt_update_prim + pt_build (upload, LBVH) + pt_render_frame + pt_read_accum into pinned host memory"},
             "gpu_launches": int(launches), "clocks": clocks,
         }
+        if multi_check is not None:
+            line["multi_gpu_check"] = multi_check
         line["roofline_fp32"] = fp32_view(r, cam, depth, line["path"]["mrays_per_s"], (clocks or {}).get("sm_mhz"))
-        if os.path.exists(tp) and tj.get("ipc_time_weighted"):
+        if tj.get("ipc_time_weighted"):
             # third view, from the same ncu capture: what the kernel is actually bound by.  4 warp-instructions can
             # issue per SM per clock; the capture says how many do and how many of an instruction's 32 lanes are alive.
             line["roofline_issue"] = {"bound": "warp-instruction issue", "achieved": tj["ipc_time_weighted"], "peak": 4.0,
@@ -414,8 +537,82 @@ def main():
             rc = ref_cuda_leg(sc, sky)
             if rc is not None:
                 line["ref_cuda_baseline"] = rc
-        print(json.dumps(line), file=real_stdout, flush=True)
+            try:
+                line["graze_c2"] = graze_leg(r, sc)
+            except Exception as e:
+                line["graze_c2"] = {"unavailable": str(e)[:200]}
     r.close()
+
+    # ---- the other BASELINE.json configs ---------------------------------------------------------------------
+    if not args.no_configs:
+        configs = {}
+        graze = world == 1 and not args.no_baselines
+        barrier()
+        if rank == 0:
+            # C1 and C3 on ONE GPU (this rank's); the other ranks wait at the barrier below
+            c1 = scenes.demo_scene(640, 360)
+            configs["C1"] = config_single_gpu("C1", "reference demo scene (floor + 74 spheres / cylinders, 4 materials, sky), 640x360, 16 spp, depth 8",
+                                              c1, sky, 16, 20, depth, stream, graze)
+            c3 = scenes.stress_field(100000, 1920, 1080)
+            configs["C3"] = config_single_gpu("C3", "BVH stress: floor + 100 k spheres / cylinders (128 836 primitives with the hollow shells), glass-heavy, 1920x1080, 32 spp, depth 8",
+                                              c3, sky, 32, 3, depth, stream, graze)
+            del c3
+        barrier()
+        # C4: 3840x2160, a FIXED 1024 spp split over the ranks (strong scaling), one reduce of the 133 MB SUM buffers
+        sc4 = scenes.sphere_field(1000, 3840, 2160)
+        r4 = api.Renderer(sc4, sky)
+        r4.set_stream(stream)
+        ptd.render_sharded(r4, sc4.camera, 16 * world, depth, seed=5, rank=rank, world=world)      # warm-up: allocations, NCCL
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ptd.render_sharded(r4, sc4.camera, 1024, depth, seed=5, rank=rank, world=world, sync=False)
+        e1.record()
+        torch.cuda.synchronize()
+        ms4 = max_over_ranks(e0.elapsed_time(e1))
+        r4.synchronize()
+        st4 = r4.stats()
+        if rank == 0:
+            configs["C4"] = {"workload": "C2 scene at 3840x2160, 1024 spp progressive (16-spp waves), depth 8; the sample range is split over the ranks, one NCCL reduce of the SUM buffers at the end",
+                             "mpaths_per_s": 3840 * 2160 * 1024 / ms4 / 1e3, "ms": ms4, "n_gpus": world, "scaling": "strong",
+                             "spp_total": 1024, "spp_per_rank": ptd.shard_samples(1024, world, 0)[1], "waves_per_rank": st4["waves"],
+                             "segments_per_path": st4["segments"] / st4["paths"], "timing": "CUDA events, max over ranks, reduce inside"}
+        r4.close()
+        barrier()
+        # C5: 120 frames at 1080p x 64 spp, camera orbit, 10 % of the spheres move: every frame is pt_update_prim x 100 +
+        # pt_build (upload + LBVH on the device) + render + read-back of the mean image; frame f belongs to rank f % N
+        r5 = api.Renderer(sc, sky)
+        r5.set_stream(stream)
+        n_frames = 120
+        cams = video.camera_path(cam, n_frames)
+        mine = ptd.frames_of_rank(n_frames, world, rank)
+        sc5 = copy.deepcopy(sc)
+
+        def frame(f):
+            ids, centres = video.moving_spheres(sc5, f)
+            for p, c in zip(ids, centres):
+                r5.update_prim(int(p), c, float(sc5.radius[p]))
+            r5.build()
+            r5.reset_accum()
+            r5.render(cams[f], spp, depth, seed=2026, sync=False)
+            r5.read_accum(host_img)
+
+        frame(mine[0] if mine else 0)
+        barrier()
+        t0 = time.perf_counter()
+        for f in mine:
+            frame(f)
+        torch.cuda.synchronize()
+        wall5 = max_over_ranks(time.perf_counter() - t0)
+        if rank == 0:
+            configs["C5"] = {"workload": "MotionalCamera video: 120 frames, 1920x1080 x 64 spp, depth 8, camera orbit + 10 % of the spheres moving, per-frame upload + LBVH rebuild, frames round-robin over the ranks, every frame read back to pinned host memory",
+                             "mpaths_per_s": n_frames * cam.width * cam.height * spp / wall5 / 1e6, "wall_s": wall5, "n_gpus": world,
+                             "frames": n_frames, "frames_per_s": n_frames / wall5, "timing": "wall clock, max over ranks"}
+        r5.close()
+        if rank == 0:
+            line["configs"] = configs
+    if rank == 0:
+        print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

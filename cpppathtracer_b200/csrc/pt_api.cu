@@ -84,6 +84,8 @@ struct pt_scene {
     std::vector<pt_material> materials;      // distinct materials, slot order
     std::map<MatKey, int> material_slots;
     bool dirty = true, built = false;
+    std::vector<uint32_t> rank_cache;        // reference leaf rank per primitive, from the last build after an add
+    bool rank_valid = false;
     // options
     uint32_t opt_wave_paths = 128u << 20;  // 64 spp per wave at 1080p: 59 GB of hit queues; 5.57 vs 5.40 Gpaths/s with 32 Mi (16 spp), 5.23 with 16 Mi
                                            // (profiles/ab/wave_sweep_v9.log); ensure_queues halves the wave until the queues fit in free memory
@@ -367,9 +369,16 @@ int upload_and_build(pt_scene* s) {
     // device order = the reference's leaf visiting order, so that exact ties resolve by index (pt_wavefront.cuh)
     std::vector<uint32_t> rank(std::max(n, 1));
     std::vector<float4> tb_mn, tb_mx;      // PT_OPT_REF_LEAF_BOXES: per device primitive, the reference parent's box
-    if ((s->opt_tie_order || s->opt_ref_leaf_boxes) && n >= 2) {
+    // The reference sorts its objects ONCE, in BuildBVH; SceneBVH::UpdateObject only refits the boxes of the tree it has
+    // (bvh.cu:122-157), so its leaf visiting order -- all that the tie rule needs -- survives every object update.
+    // pt_update_prim therefore keeps the order of the last build that followed an add; only that build pays for the
+    // host-side restatement of the reference's sort (35 ms at 128 k primitives, 43x the device LBVH).
+    if (s->opt_tie_order && !s->opt_ref_leaf_boxes && n >= 2 && s->rank_valid && (int)s->rank_cache.size() == n) {
+        rank = s->rank_cache;
+    } else if ((s->opt_tie_order || s->opt_ref_leaf_boxes) && n >= 2) {
         RefOrder ro(s->prims);
         rank = ro.ranks();
+        s->rank_cache = rank; s->rank_valid = true;
         if (!s->opt_tie_order) for (int i = 0; i < n; ++i) rank[i] = (uint32_t)i;
         if (s->opt_ref_leaf_boxes) {
             tb_mn.resize(n); tb_mx.resize(n);
@@ -955,10 +964,10 @@ int pt_set_option(pt_scene* s, int option, int64_t value) {
             if (value < 1024 || value > (1ll << 28)) return fail(PT_ERR_INVALID, "wave_paths out of range");
             s->opt_wave_paths = (uint32_t)value; return PT_OK;
         case PT_OPT_STAGE_TIMING: s->opt_stage_timing = value != 0; return PT_OK;
-        case PT_OPT_TIE_ORDER: s->opt_tie_order = value != 0; s->dirty = true; return PT_OK;
+        case PT_OPT_TIE_ORDER: s->opt_tie_order = value != 0; s->dirty = true; s->rank_valid = false; return PT_OK;
         case PT_OPT_SKY_QUARTER_ROWS: s->opt_sky_quarter = value != 0; return PT_OK;
         case PT_OPT_COUNT_STEPS: s->opt_count_steps = value != 0; return PT_OK;
-        case PT_OPT_REF_LEAF_BOXES: s->opt_ref_leaf_boxes = value != 0; s->dirty = true; return PT_OK;
+        case PT_OPT_REF_LEAF_BOXES: s->opt_ref_leaf_boxes = value != 0; s->dirty = true; s->rank_valid = false; return PT_OK;
         case PT_OPT_SAH_TREELETS: s->opt_sah_treelets = value != 0; s->dirty = true; return PT_OK;
         case PT_OPT_SAH_PASSES:
             if (value < 0 || value > 16) return fail(PT_ERR_INVALID, "PT_OPT_SAH_PASSES: 0 .. 16");
@@ -992,7 +1001,7 @@ static int add_prim(pt_scene* s, int type, const float* c, float radius, float y
     pt_material zero; memset(&zero, 0, sizeof(zero));   // the caller memsets Object to 0 (video_renderer.cpp:75,85)
     p.mat_slot = material_slot(s, zero);
     s->prims.push_back(p);
-    s->dirty = true;
+    s->dirty = true; s->rank_valid = false;
     return (int)s->prims.size() - 1;
 }
 int pt_add_sphere(pt_scene* s, const float center[3], float radius) {
@@ -1136,6 +1145,7 @@ int pt_trace_rays(pt_scene* s, int n, const float* rays8, int32_t* prim, float* 
     args.ctrl_in = s->ctrl.p; args.ctrl_out = s->ctrl.p + 1;
     args.ray_o = s->q_o.p; args.ray_d = s->q_d.p; args.ray_range = (const float2*)s->scratch_f[1].p; args.slot_hit = s->hit.p;
     args.n_rays = (uint32_t)n; args.step_counters = s->seg_counter.p + 1;
+    CK(cudaEventRecord(s->ev0, st));
     if (s->opt_count_steps) {
         CK(s->scratch_i[1].reserve(n));
         CK(cudaMemsetAsync(s->seg_counter.p, 0, 4 * sizeof(unsigned long long), st));
@@ -1144,6 +1154,8 @@ int pt_trace_rays(pt_scene* s, int n, const float* rays8, int32_t* prim, float* 
     } else {
         k_bounce<SRC_RAYS, false><<<s->grid_bounce, 32 * PT_BOUNCE_WARPS, PT_BOUNCE_SMEM, st>>>(args);
     }
+    CK(cudaEventRecord(s->ev1, st));
+    s->frame_recorded = false;
     k_unpack_hits<<<g, 256, 0, st>>>(n, scene_dev(s), s->q_o.p, s->q_d.p, s->hit.p, s->scratch_i[0].p,
                                      s->scratch_f[2].p, s->scratch_f[3].p, s->scratch_f[4].p);
     s->stats.launches += 3;
@@ -1153,6 +1165,7 @@ int pt_trace_rays(pt_scene* s, int n, const float* rays8, int32_t* prim, float* 
     if (normal3) CK(cudaMemcpyAsync(normal3, s->scratch_f[3].p, (size_t)n * 12, cudaMemcpyDeviceToHost, st));
     if (hitpos3) CK(cudaMemcpyAsync(hitpos3, s->scratch_f[4].p, (size_t)n * 12, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    CK(cudaEventElapsedTime(&s->stats.traverse_ms, s->ev0, s->ev1));      // device time of the closest-hit launch alone
     return PT_OK;
 }
 

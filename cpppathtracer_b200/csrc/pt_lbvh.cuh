@@ -502,15 +502,20 @@ __global__ void k_entry_grid(EntryGridBuild g, const float4* __restrict__ nodes)
         const bool ha = box_overlaps_block(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, bc, bh);
         const bool hb = box_overlaps_block(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, bc, bh);
         const int add = (int)ha + (int)hb;
-        if (n - 1 + add > 4) { closed |= 1u << j; continue; }
+        const int la = __float_as_int(n3.x), lb = __float_as_int(n3.y);
+        // a link to a LEAF never enters the frontier: the walk tests a primitive only after the ray has hit the
+        // primitive's own box in its parent, and the frontier must not change which primitives get tested (round-2
+        // A/B: with leaf links in the frontier the primitive tests per segment doubled and the images left the
+        // grid-less ones in the graze class)
+        if (n - 1 + add > 4 || (ha && la < 0) || (hb && lb < 0)) { closed |= 1u << j; continue; }
         // remove link j (the order of the others is kept, and with it their `closed` bits), append the children
         const uint32_t low = closed & ((1u << j) - 1u), high = (closed >> (j + 1)) << j;
         closed = low | high;
 #pragma unroll
         for (int q = 0; q < 3; ++q) if (q >= j) f[q] = f[q + 1];
         --n;
-        if (ha) { f[n] = __float_as_int(n3.x); ++n; }
-        if (hb) { f[n] = __float_as_int(n3.y); ++n; }
+        if (ha) { f[n] = la; ++n; }
+        if (hb) { f[n] = lb; ++n; }
 #pragma unroll
         for (int q = 0; q < 4; ++q) if (q >= n) f[q] = 0x7fffffff;
     }

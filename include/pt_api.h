@@ -120,7 +120,10 @@ int pt_add_platform(pt_scene* s, float y_pos);
 int pt_add_cylinder(pt_scene* s, const float center[3], float radius, float height);
 /* replaces the by-hand fill of Object::material_ (include/object.h:26) */
 int pt_set_material(pt_scene* s, int prim, const pt_material* m);
-/* replaces SceneBVH::UpdateObject (cuSrc/bvh.cu:144-157); takes effect at the next pt_build */
+/* replaces SceneBVH::UpdateObject (cuSrc/bvh.cu:144-157); takes effect at the next pt_build.  Like the reference, whose
+ * UpdateObject refits the tree it has and never re-sorts, an update keeps the order in which exactly tied hits resolve
+ * (PT_OPT_TIE_ORDER): that order is recomputed only by the first pt_build after a pt_add_* call (or after
+ * pt_set_option(PT_OPT_TIE_ORDER, 1) is set again). */
 int pt_update_prim(pt_scene* s, int prim, const float center[3], float radius, float y_pos, float height);
 /* replaces PocaTextureUtils::AddTexByFile("textures\\sky.png") (cuSrc/path_tracer.cu:47,
  * cuSrc/textures.cu:14-62) minus the OpenCV decode: the caller passes decoded RGBA8 rows */

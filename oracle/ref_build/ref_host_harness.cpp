@@ -167,6 +167,19 @@ int ref_build(void) {
     return (int)(2 * g_objs.size() - 1);
 }
 
+/* SceneBVH::UpdateObject (bvh.cu:144-157): the caller edits its Object and the reference copies it into the leaf and
+ * refits the boxes up to the root -- the tree's topology, and with it the leaf visiting order, stays as built. */
+int ref_update_object(int id, const float* center, float radius, float y_pos, float height) {
+    if (!g_built || id < 0 || id >= (int)g_objs.size()) return -1;
+    Object* o = g_objs[id];
+    o->center_ = make_float3(center[0], center[1], center[2]);
+    o->radius_ = radius;
+    if (o->type_ == PrimitiveType::Platform) o->y_pos_ = y_pos;     /* height_ carries the id */
+    else o->height_ = height;                                        /* y_pos_ carries the id */
+    SceneBVH::UpdateObject(o);
+    return 0;
+}
+
 /* Reference leaf visiting order: TraceRay (bvh.cu:167-205) pops the right son first, so among
  * exactly-tied hits the leaf met first in a right-first depth-first walk wins.  Returns, per
  * primitive id, its rank in that walk (0 = tested first). */

@@ -95,6 +95,15 @@ class RefHost:
         self.set_camera(scene.camera)
         return n_nodes
 
+    def update_object(self, prim: int, center, radius: float, y_pos: float = 0.0, height: float = 0.0):
+        """SceneBVH::UpdateObject on the reference's own tree (reference build only: refit, no re-sort)."""
+        if self.kind != "reference":
+            raise RuntimeError("update_object needs the reference build (oracle/_ref)")
+        c = (C.c_float * 3)(*[float(v) for v in center])
+        self.lib.ref_update_object.restype = C.c_int
+        if self.lib.ref_update_object(C.c_int(int(prim)), c, C.c_float(radius), C.c_float(y_pos), C.c_float(height)) != 0:
+            raise RuntimeError("ref_update_object failed")
+
     def leaf_order(self) -> np.ndarray:
         out = np.full(self.n_prims, -1, np.int32)
         self.lib.ref_leaf_order(_p(out, C.c_int32))

@@ -79,3 +79,66 @@ def test_sah_refit_lowers_cost_and_keeps_every_hit(maker, sky):
     imgt, primt, tt, stt, vt = out[-2]
     assert np.array_equal(prim0, primt) and np.array_equal(t0, tt) and np.array_equal(img0, imgt)
     assert stt["bvh_sah"] < st4["bvh_sah"] and vt < v0
+
+
+def test_update_prim_matches_the_references_own_update_object(ref_oracle, sky):
+    """pt_update_prim + pt_build against SceneBVH::UpdateObject of the reference build itself (bvh.cu:144-157: refit,
+    no re-sort), on a scene full of exact ties: cylinders standing on the floor plane and hollow glass shells.  The
+    reference's leaf visiting order survives its updates, so the product keeps the tie order of its last full build
+    -- and skips the host-side restatement of the reference's sort on every rebuild after the first."""
+    sc = scenes.demo_scene(64, 36)
+    r = api.Renderer(sc, sky)
+    ref_oracle.load_scene(sc)
+    order0 = ref_oracle.leaf_order().copy()
+    rng = np.random.RandomState(12)
+    cyl = np.where(sc.prim_type == scenes.CYLINDER)[0]
+    inner = np.where(sc.radius < 0)[0]                        # hollow shells: same centre as the primitive before them
+
+    def tie_rays():
+        rays = []
+        for c in cyl:                                          # down through a cylinder onto the floor: cap == floor plane
+            for _ in range(60):
+                ang, rad = rng.uniform(0, 2 * np.pi), rng.uniform(0, 0.9) * abs(sc.radius[c])
+                o = [sc.center[c, 0] + rad * np.cos(ang), sc.center[c, 1], sc.center[c, 2] + rad * np.sin(ang)]
+                d = np.array([rng.normal() * 0.05, -1.0, rng.normal() * 0.05]); d /= np.linalg.norm(d)
+                rays.append(o + d.tolist() + [2e-5, 1e30])
+        for c in inner:                                        # from far away through a hollow shell: inner and outer surface
+            for _ in range(60):
+                o = sc.center[c] + np.float32([rng.uniform(-1, 1) * 900, rng.uniform(200, 600), rng.uniform(-1, 1) * 900])
+                tgt = sc.center[c] + rng.normal(size=3) * abs(sc.radius[c]) * 0.5
+                d = tgt - o; d /= np.linalg.norm(d)
+                rays.append(o.tolist() + d.tolist() + [0.0, 1e30])
+        return np.array(rays, np.float32)
+
+    for step in range(3):
+        move = np.concatenate([rng.choice(cyl, 6, replace=False), rng.choice(inner, min(4, len(inner)), replace=False)])
+        for p in move:
+            delta = np.float32([rng.uniform(-30, 30), 0.0, rng.uniform(-30, 30)])
+            group = [p, p - 1] if sc.radius[p] < 0 else [p]    # a shell moves together with its outer primitive
+            for q in group:
+                sc.center[q] = sc.center[q] + delta
+                r.update_prim(int(q), sc.center[q], float(sc.radius[q]), 0.0, float(sc.height[q]))
+                ref_oracle.update_object(int(q), sc.center[q], float(sc.radius[q]), 0.0, float(sc.height[q]))
+        r.build()
+        assert np.array_equal(ref_oracle.leaf_order(), order0)          # the reference did not re-sort
+        rays = np.concatenate([tie_rays(), ref_oracle.raygen(np.stack([rng.randint(0, 64, 4000), rng.randint(0, 36, 4000)], 1),
+                                                             rng.random_sample((4000, 3)))])
+        pg, tg, ng, _ = r.trace(rays)
+        pr, tr, nr, _ = ref_oracle.trace(rays)
+        assert (sc.prim_type[pr[pr >= 0]] == scenes.PLATFORM).any() and (sc.prim_type[pr[pr >= 0]] == scenes.CYLINDER).any()
+        assert np.array_equal(pg, pr) and np.array_equal(tg, tr) and np.array_equal(ng, nr), f"step {step}: {(pg != pr).sum()} id mismatches"
+    r.close()
+
+
+def test_rebuild_after_update_is_cheap_at_100k_primitives(sky):
+    """pt_build after one pt_update_prim at C3's size: no host-side sort any more (it took 35 ms in round 1)."""
+    import time
+    sc = scenes.stress_field(100000, 320, 180)
+    r = api.Renderer(sc, sky)
+    walls = []
+    for k in range(5):
+        r.update_prim(7, sc.center[7] + np.float32([0.0, 0.0, 0.25 * k]), float(sc.radius[7]), 0.0, float(sc.height[7]))
+        t0 = time.perf_counter(); r.build(); walls.append((time.perf_counter() - t0) * 1e3)
+    r.render(sc.camera, 1, 8, seed=1)
+    assert min(walls) < 6.0, f"pt_build after an update: {walls} ms"
+    r.close()

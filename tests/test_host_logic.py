@@ -56,7 +56,17 @@ def test_product_does_not_touch_oracle():
 
 def test_struct_layouts_match_header():
     assert C.sizeof(api.PtMaterial) == 48 and C.sizeof(api.PtCamera) == 52
-    assert C.sizeof(api.PtStats) == 88
+    assert C.sizeof(api.PtStats) == 96
+    # and against the C compiler's view of include/pt_api.h
+    import subprocess, tempfile
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "s.c")
+        with open(src, "w") as f:
+            f.write('#include <stdio.h>\n#include "pt_api.h"\nint main(void){printf("%zu %zu %zu\\n", sizeof(pt_material), sizeof(pt_camera), sizeof(pt_stats));return 0;}\n')
+        exe = os.path.join(d, "s")
+        subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), src, "-o", exe], check=True)
+        sizes = [int(v) for v in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
+    assert sizes == [C.sizeof(api.PtMaterial), C.sizeof(api.PtCamera), C.sizeof(api.PtStats)]
 
 
 def test_scene_generators_are_deterministic():

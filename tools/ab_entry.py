@@ -10,9 +10,9 @@ for which in sys.argv[1:] or ["c1", "c2", "c3"]:
           "c3": lambda: scenes.stress_field(100000, 1920, 1080)}[which]()
     spp = {"c1": 64, "c2": 16, "c3": 8}[which]
     base = None
-    for levels, cpp in ((0, 2), (12, 1), (12, 2), (12, 4), (12, 8), (12, 16)):
+    for levels, cpp, run in ((0, 2, 4), (12, 2, 4), (12, 8, 4), (12, 32, 4), (12, 8, 2), (12, 8, 3), (12, 8, 6), (0, 2, 3)):
         r = api.Renderer(sc, sky)
-        r.set_option(api.PT_OPT_ENTRY_GRID, levels); r.set_option(api.PT_OPT_ENTRY_CELLS_PER_PRIM, cpp); r.build()
+        r.set_option(api.PT_OPT_ENTRY_GRID, levels); r.set_option(api.PT_OPT_ENTRY_CELLS_PER_PRIM, cpp); r.set_option(api.PT_OPT_TRAV_INNER_RUN, run); r.build()
         b = r.stats()
         for _ in range(3):
             r.reset_accum(); r.render(sc.camera, spp, 8, seed=2026)
@@ -21,7 +21,7 @@ for which in sys.argv[1:] or ["c1", "c2", "c3"]:
         if base is None:
             base = img
         same = bool(np.array_equal(base, img))
-        print(f"{which} levels {b['entry_levels']:2d} cells {b['entry_cells']:8d} (cap {cpp:2d}/prim): {st['paths'] / st['render_ms'] / 1e3:8.1f} Mpaths/s  "
+        print(f"{which} levels {b['entry_levels']:2d} cells {b['entry_cells']:8d} (cap {cpp:2d}/prim, inner run {run}): {st['paths'] / st['render_ms'] / 1e3:8.1f} Mpaths/s  "
               f"nodes/seg {cs['node_steps'] / cs['segments']:6.2f} prims/seg {cs['prim_tests'] / cs['segments']:.3f}  build {b['build_ms']:.2f} ms  identical {same}", flush=True)
         r.close()
         if levels == 0 and which == "c3":
