@@ -30,6 +30,9 @@ namespace pt {
 #ifndef PT_PREFETCH_FAR
 #define PT_PREFETCH_FAR 1
 #endif
+#ifndef PT_PAGE_WAIT_MODE
+#define PT_PAGE_WAIT_MODE 2
+#endif
 #ifndef PT_STACK_TOP
 #define PT_STACK_TOP 1
 #endif
@@ -44,7 +47,7 @@ struct Counter128 { uint32_t v; uint32_t pad[31]; };
 struct BounceCtrl {
     Counter128 in_count;            // (parity path) rays in the caller's batch
     Counter128 rays;                // rays traced as this segment (statistics)
-    Counter128 trav_head;           // unused since the fused bounce kernel (kept: layout)
+    Counter128 page_head;           // pages of the hit pool handed out to this segment's shader bins so far
     Counter128 shade_head;          // work counter of the launch that CONSUMES this block's hit queue, in 32-item chunks
     Counter128 bin_count[NUM_BINS]; // hits of this segment per shader bin
 };
@@ -316,9 +319,19 @@ __device__ __forceinline__ void lane_leaf(const SceneDev& sc, LaneRay& r, int* s
 // The launch after the last segment runs with trace = 0: it only shades what is left.
 // (v1-v4 kept rays in double-buffered HBM queues between a traverse and a shade kernel: 208 B per segment and
 // twice the launches; profiles/r01_v5_summary.md.)
+// The queues of the four shader bins share ONE pool of records, handed out in pages of PT_PAGE records: item i of bin
+// b lives in page table[b][i / PT_PAGE] of the pool.  A bin's items are numbered by one atomic counter exactly as
+// before (dense, in arrival order, a 32-item chunk never straddles two pages); the warp whose reservation contains
+// the first item of a page takes the next free page and publishes it in the table.  Round 1 gave every bin a region
+// of the whole wave's size (all rays may land in one bin): 4 x 2 x 56 B x 128 Mi = 59 GB for the default wave, now
+// 2 x 56 B x (128 Mi + 5 pages) = 15 GB.
+#define PT_PAGE_LOG 12
+#define PT_PAGE (1u << PT_PAGE_LOG)
+#define PT_NO_PAGE 0xFFFFFFFFu
 struct HitQueues {
-    float4* o; float4* d; float4* thr; uint2* hit;
-    uint32_t capacity;     // entries per bin
+    float4* o; float4* d; float4* thr; uint2* hit;   // the pool
+    uint32_t* table;        // [NUM_BINS - 1][pages_per_bin] page of the pool, PT_NO_PAGE until taken (per segment)
+    uint32_t pages_per_bin;
 };
 enum { SRC_CAMERA = 0, SRC_HITS = 1, SRC_RAYS = 2 };
 
@@ -362,7 +375,13 @@ __device__ __forceinline__ void shade_miss(const BounceArgs& a, float3 d, float3
 __device__ __forceinline__ bool shade_hit_item(const BounceArgs& a, int bin, uint32_t item, bool last_shade, float3& ray_o,
                                                float3& ray_d, float3& thr, uint32_t& pixel, uint32_t& s) {
     const SceneDev& sc = a.sc;
-    const size_t q = (size_t)(bin - 1) * a.hq_in.capacity + item;      // bin >= 1: bin 0 (miss) has no queue
+    // bin >= 1: bin 0 (miss) has no queue.  The page was published by the previous launch: a plain cached load.
+#ifdef PT_EXP_NO_CONSUMER_PAGING
+    const size_t q = (size_t)(bin - 1) * a.hq_in.pages_per_bin + item;
+#else
+    const uint32_t page = __ldg(&a.hq_in.table[(size_t)(bin - 1) * a.hq_in.pages_per_bin + (item >> PT_PAGE_LOG)]);
+    const size_t q = ((size_t)page << PT_PAGE_LOG) | (item & (PT_PAGE - 1u));
+#endif
     // streamed once: evict-first loads / stores keep the L1 and L2 lines for the BVH nodes
     const float4 o4 = __ldcs(&a.hq_in.o[q]);
     const float4 d4 = __ldcs(&a.hq_in.d[q]);
@@ -401,6 +420,18 @@ __device__ __forceinline__ bool shade_hit_item(const BounceArgs& a, int bin, uin
     return alive;
 }
 
+// Rare path of file_hit, kept out of line so that it costs the bounce kernel no registers: the page of an item has been
+// reserved by another warp that has not published it yet.
+__device__ __noinline__ uint32_t wait_for_page(const volatile uint32_t* slot) {
+    uint32_t page = *slot;
+    for (uint32_t spins = 0; page == PT_NO_PAGE; ++spins) {
+        if (spins > (1u << 24)) __trap();                  // never observed; a hang would cost more than a failed frame
+        __nanosleep(20);
+        page = *slot;
+    }
+    return page;
+}
+
 // Files the result of a traced segment: a ray that left the scene is shaded by the sky in place (its path ends), a
 // hit goes to the hit queue of its shader bin.  Called by all 32 lanes.
 __device__ __forceinline__ void file_hit(const BounceArgs& a, uint32_t lane, bool alive, float3 o, float3 d, float3 thr,
@@ -427,10 +458,43 @@ __device__ __forceinline__ void file_hit(const BounceArgs& a, uint32_t lane, boo
         if ((int)lane == b) lane_mask = m;
     }
     uint32_t base = 0u;
-    if (lane_mask) base = atomicAdd(&a.ctrl_out->bin_count[lane & 7u].v, (uint32_t)__popc(lane_mask));
+    if (lane_mask) {
+        const uint32_t n = (uint32_t)__popc(lane_mask);
+        base = atomicAdd(&a.ctrl_out->bin_count[lane & 7u].v, n);
+        // the reservation that contains the first item of a page takes the page from the pool and publishes it
+        // (n <= 32 < PT_PAGE: at most one page boundary per reservation)
+        const uint32_t pg = (base + PT_PAGE - 1u) >> PT_PAGE_LOG;
+        if ((pg << PT_PAGE_LOG) < base + n)
+            atomicExch(&a.hq_out.table[(size_t)((lane & 7u) - 1u) * a.hq_out.pages_per_bin + pg], atomicAdd(&a.ctrl_out->page_head.v, 1u));
+    }
     base = __shfl_sync(PT_FULL, base, obin & 7);
     if (obin >= 0) {
-        const size_t j = (size_t)(obin - 1) * a.hq_out.capacity + base + __popc(my_mask & ((1u << lane) - 1u));
+        const uint32_t item = base + (uint32_t)__popc(my_mask & ((1u << lane) - 1u));
+        // the page of this item: published above by this warp, or by the warp whose reservation crossed into it -- that
+        // warp is past its atomicAdd and a few instructions away from the atomicExch, so the wait is an L2 round trip
+        const volatile uint32_t* slot = a.hq_out.table + (size_t)(obin - 1) * a.hq_out.pages_per_bin + (item >> PT_PAGE_LOG);
+#if PT_PAGE_WAIT_MODE == 0
+        uint32_t page;
+        do { page = *slot; } while (page == PT_NO_PAGE);
+#elif PT_PAGE_WAIT_MODE == 3
+        uint32_t page = *slot;
+#elif PT_PAGE_WAIT_MODE == 4
+        uint32_t page = __ldcg((const uint32_t*)slot);
+#elif PT_PAGE_WAIT_MODE == 1
+        uint32_t page = *slot;
+        if (page == PT_NO_PAGE) page = wait_for_page(slot);
+#else
+        uint32_t page = *slot;
+        for (uint32_t spins = 0; page == PT_NO_PAGE; ++spins) {
+            if (spins > (1u << 24)) __trap();
+            page = *slot;
+        }
+#endif
+#ifdef PT_EXP_NO_PRODUCER_PAGING
+        const size_t j = (size_t)(obin - 1) * a.hq_out.pages_per_bin + item + (page & 1u);
+#else
+        const size_t j = ((size_t)page << PT_PAGE_LOG) | (item & (PT_PAGE - 1u));
+#endif
         __stcs(&a.hq_out.o[j], make_float4(o.x, o.y, o.z, __uint_as_float(pixel)));
         __stcs(&a.hq_out.d[j], make_float4(d.x, d.y, d.z, __uint_as_float(s)));
         __stcs(&a.hq_out.thr[j], make_float4(thr.x, thr.y, thr.z, 0.f));
@@ -448,16 +512,20 @@ __global__ void PT_BOUNCE_BOUNDS k_bounce(const BounceArgs a) {
     const uint32_t lane = threadIdx.x & 31u;
     const SceneDev& sc = a.sc;
     // ---- work list: 32-item chunks; SRC_HITS chunks never straddle two shader bins ----
-    uint32_t chunk_end[NUM_BINS], bin_n[NUM_BINS];
+    // (the per-bin bounds live in shared memory: ten registers less across the whole persistent loop, which keeps the
+    // kernel at 56 registers = 9 CTAs per SM)
+    __shared__ uint32_t chunk_end[NUM_BINS], bin_n[NUM_BINS];
     uint32_t total = 0;
     if (SRC == SRC_HITS) {
-#pragma unroll
-        for (int b = 0; b < NUM_BINS; ++b) { bin_n[b] = a.ctrl_in->bin_count[b].v; total += (bin_n[b] + 31u) >> 5; chunk_end[b] = total; }
+        if (threadIdx.x == 0) {
+            uint32_t t = 0;
+            for (int b = 0; b < NUM_BINS; ++b) { bin_n[b] = a.ctrl_in->bin_count[b].v; t += (bin_n[b] + 31u) >> 5; chunk_end[b] = t; }
+        }
+        __syncthreads();
+        total = chunk_end[NUM_BINS - 1];
     } else {
         const uint32_t n = SRC == SRC_CAMERA ? a.n_paths : a.n_rays;
         total = (n + 31u) >> 5;
-#pragma unroll
-        for (int b = 0; b < NUM_BINS; ++b) { bin_n[b] = n; chunk_end[b] = total; }
     }
     const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
     uint32_t grab = total / (n_warps * 8u);          // chunks per atomic: keeps the head counter cold, balances the tail

@@ -378,11 +378,12 @@ def test_reference_cuda_kernels_agree(sky):
     r.close()
 
 
-@pytest.mark.parametrize("w,h,spp,bound", [(160, 90, 1024, 1.0e-3), (96, 54, 4096, 5.0e-4)])
+@pytest.mark.parametrize("w,h,spp,bound", [(160, 90, 1024, 1.0e-3), (96, 54, 4096, 5.0e-4), (640, 360, 4096, 5.0e-4)])
 def test_level3_converged_image(w, h, spp, bound, oracle, sky):
     """Convergence of the image error with spp: RMSE falls as 1/sqrt(spp) from the per-sample 1.0e-2.  north_star asks
     for RMSE <= 1e-3 and channel means within 0.5 % at 4096 spp: met at 1024 spp already, and with a factor of two to
-    spare at 4096 spp (the demo scene, every material, the sky)."""
+    spare at 4096 spp (the demo scene, every material, the sky).  The last case is config C1 at its own size, 640x360,
+    against the reference build's render of the same scene (944 M paths: about a minute of the box's host cores)."""
     sc = scenes.demo_scene(w, h)
     img, ref, st, ost = _render_pair(sc, sky, oracle, spp, seed=23)
     rmse = float(np.sqrt(np.mean((img[..., :3] - ref) ** 2)))
@@ -429,6 +430,23 @@ def test_full_size_stress_scene_c3(oracle, port_oracle, sky):
     assert np.array_equal(a, r.read_accum())
     assert np.isfinite(a).all()
     r.close()
+
+
+def test_level3_image_c3_full_scene(oracle, sky):
+    """Config C3's scene (all 128 836 primitives, glass-heavy) at image level against the reference build: reduced
+    resolution so that the host render takes seconds, same camera, same Philox stream.  Beyond the 1.6e-2 / sqrt(spp) of
+    the other scenes the bound leaves room for the graze class, which on this scene changes ~2.5e-4 of the hits
+    (north_star: excluded and counted -- bench.py prints the count per config)."""
+    sc = scenes.stress_field(100000, 240, 136)
+    spp = 64
+    img, ref, st, ost = _render_pair(sc, sky, oracle, spp, seed=31)
+    assert (img[..., 3] == spp).all()
+    rmse = float(np.sqrt(np.mean((img[..., :3] - ref) ** 2)))
+    gm, rm = img[..., :3].mean(axis=(0, 1)), ref.mean(axis=(0, 1))
+    print(f"C3 scene at 240x136 x {spp} spp: rmse {rmse:.3e}, means {gm} vs {rm}")
+    assert rmse <= 2.0e-2 / np.sqrt(spp), f"rmse {rmse:.3e}"
+    assert np.all(np.abs(gm - rm) <= 0.005 * rm), f"channel means {gm} vs {rm}"
+    assert 0.90 * ost["segments"] <= st["segments"] <= 1.002 * ost["segments"]
 
 
 def test_4k_frame_properties_c4(sky):
