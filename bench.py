@@ -40,11 +40,11 @@ WORKLOAD = {"workload": "C2: floor + 1000 mixed-material spheres, 1920x1080, 64 
 #   a wavefront design that keeps rays in HBM moves 144 B per path segment + 16 B per path.  That is the
 #     contract's algorithmic figure and what `roofline.frac` is computed from.
 #   This kernel's own traffic: rays never leave registers, a segment that leaves the scene is shaded where it ends, so
-#     only a segment THAT HITS costs one 56-byte hit record written by the launch that traces it and read by the launch
-#     that shades it (112 B), plus 16 B of radiance per path.  Reported as `roofline_own_bytes`; ncu's measured DRAM
+#     only a segment THAT HITS costs one 48-byte hit record written by the launch that traces it and read by the launch
+#     that shades it (96 B), plus 16 B of radiance per path.  Reported as `roofline_own_bytes`; ncu's measured DRAM
 #     bytes agree with this model to 4 %.
 SURVEY_BYTES_PER_SEGMENT = 144
-OWN_BYTES_PER_HIT_RECORD = 112
+OWN_BYTES_PER_HIT_RECORD = 96
 BYTES_PER_PATH = 16
 
 
@@ -511,7 +511,7 @@ def main():
                                  "the bytes this model budgets (see roofline_own_bytes) because rays stay in registers"},
             "roofline_own_bytes": {"bound": "hbm", "achieved": achieved_own, "peak": peak, "unit": "GB/s",
                                    "frac": (achieved_own / peak) if achieved_own else None,
-                                   "byte_model": "this kernel's own traffic: 112 B per segment that hits (one 56-byte hit record written + read) + 16 B per path",
+                                   "byte_model": "this kernel's own traffic: 96 B per segment that hits (one 48-byte hit record written + read) + 16 B per path",
                                    "hit_records_per_step": hits, "bytes_per_launch": own_bytes / n_launch,
                                    "measured_over_model": (traffic * n_launch / own_bytes) if traffic else None},
             "path": {"mrays_per_s": segs / (st["render_ms"] * 1e-3) / 1e6 if st["render_ms"] > 0 else None,

@@ -87,8 +87,8 @@ struct pt_scene {
     std::vector<uint32_t> rank_cache;        // reference leaf rank per primitive, from the last build after an add
     bool rank_valid = false;
     // options
-    uint32_t opt_wave_paths = 128u << 20;  // 64 spp per wave at 1080p: 15 GB of hit-record pool + 2 GB of path radiance; 5.57 vs 5.40 Gpaths/s with
-                                           // 32 Mi (16 spp), 5.23 with 16 Mi (profiles/ab/wave_sweep_v9.log); ensure_queues halves the wave until it fits in free memory
+    uint32_t opt_wave_paths = 128u << 20;  // 64 spp per wave at 1080p: 26 GB of hit queues; 5.57 vs 5.40 Gpaths/s with 32 Mi (16 spp), 5.23 with 16 Mi
+                                           // (profiles/ab/wave_sweep_v9.log); ensure_queues halves the wave until the queues fit in free memory
     int opt_stage_timing = 0;
     int opt_tie_order = 1;
     int opt_sky_quarter = 1;
@@ -119,12 +119,10 @@ struct pt_scene {
     DevBuf<float4> accum;
     // wave queues
     DevBuf<float4> path_out;
-    DevBuf<float4> hq_o[2], hq_d[2], hq_thr[2];   // hit queues, double-buffered over segments
-    DevBuf<uint2> hq_hit[2];
+    DevBuf<float4> hq_p[2], hq_d[2], hq_thr[2];   // hit queues (two two-ended regions each), double-buffered over segments
     DevBuf<float4> q_o, q_d;                      // parity path only: the caller's ray batch
     DevBuf<uint2> hit;                            // parity path only: results by ray slot
     DevBuf<BounceCtrl> ctrl;
-    DevBuf<uint32_t> page_table;
     DevBuf<unsigned long long> seg_counter;
     uint32_t capacity = 0;
     // parity scratch
@@ -524,33 +522,28 @@ int ensure_frame(pt_scene* s, int w, int h) {
     return PT_OK;
 }
 
-// records of the pool that holds the hit queues of one segment of a `cap`-path wave: every hit once, plus the
-// partly filled last page of each shader bin, plus one page of slack
-size_t pool_records(uint32_t cap) { return (size_t)cap + (size_t)NUM_BINS * PT_PAGE; }
-uint32_t pages_per_bin(uint32_t cap) { return cap / PT_PAGE + 2u; }
-
 cudaError_t try_reserve_wave(pt_scene* s, uint32_t cap) {
     if (cap <= s->capacity) return cudaSuccess;
     // released first so that growing never holds two copies
     s->path_out.release();
-    for (int k = 0; k < 2; ++k) { s->hq_o[k].release(); s->hq_d[k].release(); s->hq_thr[k].release(); s->hq_hit[k].release(); }
+    for (int k = 0; k < 2; ++k) { s->hq_p[k].release(); s->hq_d[k].release(); s->hq_thr[k].release(); }
     s->capacity = 0;
     cudaError_t e = s->path_out.reserve(cap);
     for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
-        e = s->hq_o[k].reserve(pool_records(cap));
-        if (e == cudaSuccess) e = s->hq_d[k].reserve(pool_records(cap));
-        if (e == cudaSuccess) e = s->hq_thr[k].reserve(pool_records(cap));
-        if (e == cudaSuccess) e = s->hq_hit[k].reserve(pool_records(cap));
+        // two regions of `cap` records, each shared by two shader bins growing from its ends (HitQueues)
+        e = s->hq_p[k].reserve(2 * (size_t)cap);
+        if (e == cudaSuccess) e = s->hq_d[k].reserve(2 * (size_t)cap);
+        if (e == cudaSuccess) e = s->hq_thr[k].reserve(2 * (size_t)cap);
     }
     if (e == cudaSuccess) { s->capacity = cap; return e; }
     s->path_out.release();
-    for (int k = 0; k < 2; ++k) { s->hq_o[k].release(); s->hq_d[k].release(); s->hq_thr[k].release(); s->hq_hit[k].release(); }
+    for (int k = 0; k < 2; ++k) { s->hq_p[k].release(); s->hq_d[k].release(); s->hq_thr[k].release(); }
     cudaGetLastError();   // clear the sticky allocation error before the caller retries with a smaller wave
     return e;
 }
 
 // Sizes the wave: as many samples per pixel as fit PT_OPT_WAVE_PATHS, halved until the hit queues fit in free
-// device memory (a 32 Mi-path wave reserves 19 GB; another tenant of the GPU must not make the frame fail).
+// device memory (the default 128 Mi-path wave reserves 26 GB; another tenant of the GPU must not make the frame fail).
 int ensure_queues(pt_scene* s, uint32_t npix, uint32_t& spp_per_wave, int max_depth) {
     while (true) {
         cudaError_t e = try_reserve_wave(s, npix * spp_per_wave);
@@ -561,17 +554,11 @@ int ensure_queues(pt_scene* s, uint32_t npix, uint32_t& spp_per_wave, int max_de
     }
     CK(s->ctrl.reserve((size_t)max_depth + 3));
     CK(s->seg_counter.reserve(4));
-    // one page table per segment (cleared once per wave, with the control blocks)
-    CK(s->page_table.reserve((size_t)(max_depth + 1) * (NUM_BINS - 1) * pages_per_bin(s->capacity)));
     return PT_OK;
 }
 
-// hit queues of segment `seg`: the pools are double-buffered over segments, the page tables are per segment
-HitQueues hit_queues(pt_scene* s, int seg) {
-    const int k = seg & 1;
-    HitQueues hq; hq.o = s->hq_o[k].p; hq.d = s->hq_d[k].p; hq.thr = s->hq_thr[k].p; hq.hit = s->hq_hit[k].p;
-    hq.pages_per_bin = pages_per_bin(s->capacity);
-    hq.table = s->page_table.p + (size_t)seg * (NUM_BINS - 1) * hq.pages_per_bin;
+HitQueues hit_queues(pt_scene* s, int k) {
+    HitQueues hq; hq.p = s->hq_p[k].p; hq.d = s->hq_d[k].p; hq.thr = s->hq_thr[k].p; hq.capacity = s->capacity;
     return hq;
 }
 
@@ -626,7 +613,6 @@ int render_async(pt_scene* s, const pt_camera* cam, int spp, int max_depth, uint
         const uint32_t ns = std::min<uint32_t>(spp_per_wave, (uint32_t)spp - s0);
         const uint32_t n_paths = npix * ns;
         CK(cudaMemsetAsync(s->ctrl.p, 0, ((size_t)max_depth + 2) * sizeof(BounceCtrl), st));
-        CK(cudaMemsetAsync(s->page_table.p, 0xFF, (size_t)(max_depth + 1) * (NUM_BINS - 1) * pages_per_bin(s->capacity) * sizeof(uint32_t), st));
         args.first_sample = first_sample + s0; args.n_paths = n_paths;
         // segment 0: camera rays -> hit queue 0
         CK(stage_event());
@@ -644,7 +630,7 @@ int render_async(pt_scene* s, const pt_camera* cam, int spp, int max_depth, uint
             args.drop_last_hits = (drop_last && k == max_depth - 1) ? 1 : 0;
             args.segment = k; args.trace = k < max_depth ? 1 : 0;
             args.ctrl_in = ctrl + (k - 1); args.ctrl_out = ctrl + k;
-            args.hq_in = hit_queues(s, k - 1); args.hq_out = hit_queues(s, k);
+            args.hq_in = hit_queues(s, (k - 1) & 1); args.hq_out = hit_queues(s, k & 1);
             launch_bounce<SRC_HITS>(s, args, st);
         }
         CK(stage_event());
@@ -956,9 +942,9 @@ void pt_scene_destroy(pt_scene* s) {
     s->bvh_prims.release(); s->parent_inner.release(); s->parent_leaf.release(); s->flags.release(); s->children.release();
     s->codes.release(); s->codes_sorted.release(); s->ids.release(); s->ids_sorted.release(); s->bounds6.release();
     s->orig_id.release(); s->cub_tmp.release(); s->accum.release(); s->read_tmp.release(); s->path_out.release(); s->hit.release();
-    s->ctrl.release(); s->page_table.release(); s->q_o.release(); s->q_d.release(); s->seg_counter.release();
+    s->ctrl.release(); s->q_o.release(); s->q_d.release(); s->seg_counter.release();
     s->node_height.release(); s->sah_dev.release(); s->grid_cells.release(); s->grid_levels.release();
-    for (int k = 0; k < 2; ++k) { s->hq_o[k].release(); s->hq_d[k].release(); s->hq_thr[k].release(); s->hq_hit[k].release(); s->scratch_i[k].release(); }
+    for (int k = 0; k < 2; ++k) { s->hq_p[k].release(); s->hq_d[k].release(); s->hq_thr[k].release(); s->scratch_i[k].release(); }
     for (auto& b : s->scratch_f) b.release();
     s->disp_color.release(); s->disp_normal.release(); s->disp_mix.release(); s->disp_depth.release(); s->disp_bgra.release();
     // display path: the scene-owned page-locked frames (the reference's output_buffer_, path_tracer.cu:303-304, lives as

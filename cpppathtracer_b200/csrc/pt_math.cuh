@@ -142,15 +142,18 @@ __device__ __forceinline__ bool hit_cylinder(float4 g0, float height, float3 o, 
 }
 
 // attr.hit_pos / attr.normal of the winning test (object.cu:21-23,29-30,42-43,61-62,75-76,96-98,105-107)
-__device__ __forceinline__ void hit_attributes(float4 g0, int part, float3 o, float3 d, float t, float3& pos,
-                                               float3& normal) {
-    pos = o + t * d;
+__device__ __forceinline__ void hit_normal(float4 g0, int part, float3 pos, float3 d, float3& normal) {
     switch (part) {
         case PART_SPHERE_NEAR: normal = (pos - f3(g0.x, g0.y, g0.z)) / g0.w; break;   // signed radius
         case PART_SPHERE_FAR: normal = normalize(pos - f3(g0.x, g0.y, g0.z)); break;
         case PART_CYL_SIDE: normal = normalize(f3(pos.x - g0.x, 0.f, pos.z - g0.z)); break;
         default: normal = normalize(f3(0.f, -d.y, 0.f)); break;                       // platform and caps
     }
+}
+__device__ __forceinline__ void hit_attributes(float4 g0, int part, float3 o, float3 d, float t, float3& pos,
+                                               float3& normal) {
+    pos = o + t * d;
+    hit_normal(g0, part, pos, d, normal);
 }
 
 // ---- shading ----------------------------------------------------------------------------------------

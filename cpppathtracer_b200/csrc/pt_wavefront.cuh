@@ -30,9 +30,6 @@ namespace pt {
 #ifndef PT_PREFETCH_FAR
 #define PT_PREFETCH_FAR 1
 #endif
-#ifndef PT_PAGE_WAIT_MODE
-#define PT_PAGE_WAIT_MODE 2
-#endif
 #ifndef PT_STACK_TOP
 #define PT_STACK_TOP 1
 #endif
@@ -47,7 +44,7 @@ struct Counter128 { uint32_t v; uint32_t pad[31]; };
 struct BounceCtrl {
     Counter128 in_count;            // (parity path) rays in the caller's batch
     Counter128 rays;                // rays traced as this segment (statistics)
-    Counter128 page_head;           // pages of the hit pool handed out to this segment's shader bins so far
+    Counter128 trav_head;           // unused since the fused bounce kernel (kept: layout)
     Counter128 shade_head;          // work counter of the launch that CONSUMES this block's hit queue, in 32-item chunks
     Counter128 bin_count[NUM_BINS]; // hits of this segment per shader bin
 };
@@ -313,26 +310,29 @@ __device__ __forceinline__ void lane_leaf(const SceneDev& sc, LaneRay& r, int* s
 //   SRC_CAMERA : path ids        -> MotionalCamera::RayGen                      -> trace segment 0
 //   SRC_HITS   : hit queue k-1   -> shade (one shader per chunk)                -> trace segment k (survivors)
 //   SRC_RAYS   : caller's rays   (parity entry point pt_trace_rays)             -> trace, results by ray slot
-// Rays never touch HBM: the only stage-to-stage traffic is the hit queue, one 56-byte record per segment,
+// Rays never touch HBM: the only stage-to-stage traffic is the hit queue, one 48-byte record per segment that hits,
 // SoA float4, written and read in order:
-//   hq.o = (origin, bits pixel)  hq.d = (dir, bits sample)  hq.thr = (throughput)  hq.hit = (bits t, prim<<3|part)
+//   hq.p = (hit position, bits pixel)  hq.d = (dir, bits sample)  hq.thr = (throughput, bits prim<<3|part)
+// (round 1 stored origin and t, 56 bytes; the position origin + t*dir is the same float whichever launch adds it up)
 // The launch after the last segment runs with trace = 0: it only shades what is left.
 // (v1-v4 kept rays in double-buffered HBM queues between a traverse and a shade kernel: 208 B per segment and
 // twice the launches; profiles/r01_v5_summary.md.)
-// The queues of the four shader bins share ONE pool of records, handed out in pages of PT_PAGE records: item i of bin
-// b lives in page table[b][i / PT_PAGE] of the pool.  A bin's items are numbered by one atomic counter exactly as
-// before (dense, in arrival order, a 32-item chunk never straddles two pages); the warp whose reservation contains
-// the first item of a page takes the next free page and publishes it in the table.  Round 1 gave every bin a region
-// of the whole wave's size (all rays may land in one bin): 4 x 2 x 56 B x 128 Mi = 59 GB for the default wave, now
-// 2 x 56 B x (128 Mi + 5 pages) = 15 GB.
-#define PT_PAGE_LOG 12
-#define PT_PAGE (1u << PT_PAGE_LOG)
-#define PT_NO_PAGE 0xFFFFFFFFu
+// Layout: the four shader bins share TWO regions of `capacity` records each, one bin growing up from either end of a
+// region (bins 1, 2 in the first, bins 3, 4 in the second).  The two bins of a region can never collide -- together
+// they hold at most one record per path of the wave -- and an address is base + direction * item: no tables, no
+// allocation.  Round 1 gave every bin a region of its own (all rays may land in one bin): 4 x 2 buffers x 56 B x 128 Mi
+// = 59 GB for the default wave; now 2 x 2 x 48 B x 128 Mi = 26 GB.  (A paged pool shared by all four bins, 16 GB, was
+// built and measured: correct, but 6 % slower -- the loop that waits for a page to be published costs the kernel the
+// 9th CTA per SM; profiles/ab/r2_paged_pool.log)
 struct HitQueues {
-    float4* o; float4* d; float4* thr; uint2* hit;   // the pool
-    uint32_t* table;        // [NUM_BINS - 1][pages_per_bin] page of the pool, PT_NO_PAGE until taken (per segment)
-    uint32_t pages_per_bin;
+    float4* p; float4* d; float4* thr;
+    uint32_t capacity;     // records per region
 };
+__device__ __forceinline__ size_t hit_slot(uint32_t capacity, int bin, uint32_t item) {
+    // bin 1: 0 + i   bin 2: cap-1 - i   bin 3: cap + i   bin 4: 2cap-1 - i
+    const size_t region = bin > 2 ? (size_t)capacity : (size_t)0;
+    return region + ((bin & 1) ? (size_t)item : (size_t)(capacity - 1u - item));
+}
 enum { SRC_CAMERA = 0, SRC_HITS = 1, SRC_RAYS = 2 };
 
 struct BounceArgs {
@@ -375,33 +375,28 @@ __device__ __forceinline__ void shade_miss(const BounceArgs& a, float3 d, float3
 __device__ __forceinline__ bool shade_hit_item(const BounceArgs& a, int bin, uint32_t item, bool last_shade, float3& ray_o,
                                                float3& ray_d, float3& thr, uint32_t& pixel, uint32_t& s) {
     const SceneDev& sc = a.sc;
-    // bin >= 1: bin 0 (miss) has no queue.  The page was published by the previous launch: a plain cached load.
-#ifdef PT_EXP_NO_CONSUMER_PAGING
-    const size_t q = (size_t)(bin - 1) * a.hq_in.pages_per_bin + item;
-#else
-    const uint32_t page = __ldg(&a.hq_in.table[(size_t)(bin - 1) * a.hq_in.pages_per_bin + (item >> PT_PAGE_LOG)]);
-    const size_t q = ((size_t)page << PT_PAGE_LOG) | (item & (PT_PAGE - 1u));
-#endif
+    const size_t q = hit_slot(a.hq_in.capacity, bin, item);            // bin >= 1: bin 0 (miss) has no queue
     // streamed once: evict-first loads / stores keep the L1 and L2 lines for the BVH nodes
-    const float4 o4 = __ldcs(&a.hq_in.o[q]);
+    const float4 p4 = __ldcs(&a.hq_in.p[q]);
     const float4 d4 = __ldcs(&a.hq_in.d[q]);
     const float4 t4 = __ldcs(&a.hq_in.thr[q]);
-    const uint2 h = __ldcs(&a.hq_in.hit[q]);
-    pixel = __float_as_uint(o4.w);
+    pixel = __float_as_uint(p4.w);
     s = __float_as_uint(d4.w);
+    const uint32_t code = __float_as_uint(t4.w);
     const size_t pid = (size_t)s * a.npix + pixel;
-    const float3 o = f3(o4.x, o4.y, o4.z), d = f3(d4.x, d4.y, d4.z);
+    const float3 d = f3(d4.x, d4.y, d4.z);
     thr = f3(t4.x, t4.y, t4.z);
     // Bin 0 has no queue, so this branch is never taken; it stays because ptxas allocates 56 registers with it and 58
     // without (8 instead of 9 CTAs per SM: -2.2 % on C2, same-box A/B profiles/ab/variants_r2f.log).  The Makefile
     // checks the register count of this kernel after every build.
     if (bin == BIN_MISS) { shade_miss(a, d, thr, pid, a.segment == 1); return false; }
-    const uint32_t prim = h.y >> 3;
+    const uint32_t prim = code >> 3;
     const float4 g0 = __ldg(&sc.geo0[prim]);
     const uint32_t mslot = __float_as_uint(__ldg(&sc.geo1[prim]).w) & 0x0fffffffu;
     const MaterialRec m = sc.mats[mslot];
-    float3 pos, normal;
-    hit_attributes(g0, (int)(h.y & 7u), o, d, __uint_as_float(h.x), pos, normal);
+    const float3 pos = f3(p4.x, p4.y, p4.z);
+    float3 normal;
+    hit_normal(g0, (int)(code & 7u), pos, d, normal);
     if (a.gbuf_normal != nullptr && a.segment == 1) a.gbuf_normal[pid] = make_float4(normal.x, normal.y, normal.z, 0.f);
     const float4 U = philox_uniform4(a.key, pixel, a.first_sample + s, (uint32_t)a.segment);   // slot 1 + (k-1)
     Scatter sct;
@@ -418,18 +413,6 @@ __device__ __forceinline__ bool shade_hit_item(const BounceArgs& a, int bin, uin
     if (!alive && !sc.has_emitters) a.path_out[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (alive) { ray_o = pos; ray_d = normalize(sct.bounce); }
     return alive;
-}
-
-// Rare path of file_hit, kept out of line so that it costs the bounce kernel no registers: the page of an item has been
-// reserved by another warp that has not published it yet.
-__device__ __noinline__ uint32_t wait_for_page(const volatile uint32_t* slot) {
-    uint32_t page = *slot;
-    for (uint32_t spins = 0; page == PT_NO_PAGE; ++spins) {
-        if (spins > (1u << 24)) __trap();                  // never observed; a hang would cost more than a failed frame
-        __nanosleep(20);
-        page = *slot;
-    }
-    return page;
 }
 
 // Files the result of a traced segment: a ray that left the scene is shaded by the sky in place (its path ends), a
@@ -458,47 +441,14 @@ __device__ __forceinline__ void file_hit(const BounceArgs& a, uint32_t lane, boo
         if ((int)lane == b) lane_mask = m;
     }
     uint32_t base = 0u;
-    if (lane_mask) {
-        const uint32_t n = (uint32_t)__popc(lane_mask);
-        base = atomicAdd(&a.ctrl_out->bin_count[lane & 7u].v, n);
-        // the reservation that contains the first item of a page takes the page from the pool and publishes it
-        // (n <= 32 < PT_PAGE: at most one page boundary per reservation)
-        const uint32_t pg = (base + PT_PAGE - 1u) >> PT_PAGE_LOG;
-        if ((pg << PT_PAGE_LOG) < base + n)
-            atomicExch(&a.hq_out.table[(size_t)((lane & 7u) - 1u) * a.hq_out.pages_per_bin + pg], atomicAdd(&a.ctrl_out->page_head.v, 1u));
-    }
+    if (lane_mask) base = atomicAdd(&a.ctrl_out->bin_count[lane & 7u].v, (uint32_t)__popc(lane_mask));
     base = __shfl_sync(PT_FULL, base, obin & 7);
     if (obin >= 0) {
-        const uint32_t item = base + (uint32_t)__popc(my_mask & ((1u << lane) - 1u));
-        // the page of this item: published above by this warp, or by the warp whose reservation crossed into it -- that
-        // warp is past its atomicAdd and a few instructions away from the atomicExch, so the wait is an L2 round trip
-        const volatile uint32_t* slot = a.hq_out.table + (size_t)(obin - 1) * a.hq_out.pages_per_bin + (item >> PT_PAGE_LOG);
-#if PT_PAGE_WAIT_MODE == 0
-        uint32_t page;
-        do { page = *slot; } while (page == PT_NO_PAGE);
-#elif PT_PAGE_WAIT_MODE == 3
-        uint32_t page = *slot;
-#elif PT_PAGE_WAIT_MODE == 4
-        uint32_t page = __ldcg((const uint32_t*)slot);
-#elif PT_PAGE_WAIT_MODE == 1
-        uint32_t page = *slot;
-        if (page == PT_NO_PAGE) page = wait_for_page(slot);
-#else
-        uint32_t page = *slot;
-        for (uint32_t spins = 0; page == PT_NO_PAGE; ++spins) {
-            if (spins > (1u << 24)) __trap();
-            page = *slot;
-        }
-#endif
-#ifdef PT_EXP_NO_PRODUCER_PAGING
-        const size_t j = (size_t)(obin - 1) * a.hq_out.pages_per_bin + item + (page & 1u);
-#else
-        const size_t j = ((size_t)page << PT_PAGE_LOG) | (item & (PT_PAGE - 1u));
-#endif
-        __stcs(&a.hq_out.o[j], make_float4(o.x, o.y, o.z, __uint_as_float(pixel)));
+        const size_t j = hit_slot(a.hq_out.capacity, obin, base + (uint32_t)__popc(my_mask & ((1u << lane) - 1u)));
+        const float3 pos = o + best_t * d;                           // attr.hit_pos of the winning test (object.cu:21,29,42,...)
+        __stcs(&a.hq_out.p[j], make_float4(pos.x, pos.y, pos.z, __uint_as_float(pixel)));
         __stcs(&a.hq_out.d[j], make_float4(d.x, d.y, d.z, __uint_as_float(s)));
-        __stcs(&a.hq_out.thr[j], make_float4(thr.x, thr.y, thr.z, 0.f));
-        __stcs(&a.hq_out.hit[j], make_uint2(__float_as_uint(best_t), best_code));
+        __stcs(&a.hq_out.thr[j], make_float4(thr.x, thr.y, thr.z, __uint_as_float(best_code)));
     }
 }
 
@@ -512,20 +462,16 @@ __global__ void PT_BOUNCE_BOUNDS k_bounce(const BounceArgs a) {
     const uint32_t lane = threadIdx.x & 31u;
     const SceneDev& sc = a.sc;
     // ---- work list: 32-item chunks; SRC_HITS chunks never straddle two shader bins ----
-    // (the per-bin bounds live in shared memory: ten registers less across the whole persistent loop, which keeps the
-    // kernel at 56 registers = 9 CTAs per SM)
-    __shared__ uint32_t chunk_end[NUM_BINS], bin_n[NUM_BINS];
+    uint32_t chunk_end[NUM_BINS], bin_n[NUM_BINS];
     uint32_t total = 0;
     if (SRC == SRC_HITS) {
-        if (threadIdx.x == 0) {
-            uint32_t t = 0;
-            for (int b = 0; b < NUM_BINS; ++b) { bin_n[b] = a.ctrl_in->bin_count[b].v; t += (bin_n[b] + 31u) >> 5; chunk_end[b] = t; }
-        }
-        __syncthreads();
-        total = chunk_end[NUM_BINS - 1];
+#pragma unroll
+        for (int b = 0; b < NUM_BINS; ++b) { bin_n[b] = a.ctrl_in->bin_count[b].v; total += (bin_n[b] + 31u) >> 5; chunk_end[b] = total; }
     } else {
         const uint32_t n = SRC == SRC_CAMERA ? a.n_paths : a.n_rays;
         total = (n + 31u) >> 5;
+#pragma unroll
+        for (int b = 0; b < NUM_BINS; ++b) { bin_n[b] = n; chunk_end[b] = total; }
     }
     const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
     uint32_t grab = total / (n_warps * 8u);          // chunks per atomic: keeps the head counter cold, balances the tail
