@@ -97,7 +97,8 @@ struct pt_scene {
     int opt_inner_run = 4;
     int opt_sah_treelets = 0;      // 1: the refit passes restructure 7-leaf treelets by dynamic programming (slower build, lower SAH)
     int opt_sah_passes = 4;        // SAH refit passes (tree rotations) after the Karras build; 0: plain LBVH
-    int opt_entry_grid = 12;       // finest level the entry grid may use (0: no grid, every walk starts at the root)
+    int opt_entry_grid = 0;        // finest level the entry grid may use (0, the default: no grid, every walk starts at the root;
+                                   // the grid halves the node visits per ray but not the warp's longest walk: DESIGN.md section 3.4)
     int opt_entry_cells_per_prim = 2;   // the finest level has at most this many blocks per primitive
     // device scene
     DevBuf<float4> geo0, geo1, nodes, leaf_mn, leaf_mx, leaf_c, inner_mn, inner_mx, test_mn, test_mx;

@@ -94,10 +94,13 @@ enum {
     PT_OPT_COUNT_STEPS = 8,     /* 1: use the instrumented traversal kernel that counts node visits / primitive tests */
     PT_OPT_TRAV_INNER_RUN = 7,  /* tuning: inner-node steps a lane may take before the warp regroups for leaf tests */
     PT_OPT_SAH_PASSES = 10,     /* SAH refit passes (tree rotations) after the LBVH build; default 4, 0 = plain LBVH */
-    PT_OPT_ENTRY_GRID = 12,     /* finest level of the ENTRY GRID (default 12; 0: off, every walk starts at the root).  Level l
+    PT_OPT_ENTRY_GRID = 12,     /* finest level of the ENTRY GRID (default 0: off, every walk starts at the root; 12 = as fine as the
+                                   scene allows).  Level l
                                    tiles the scene's box with overlapping 2x2x2 blocks of cubic cells of 2^-l of its size; a
                                    block stores the <= 4 tree links a ray segment inside it has to start from, so short rays
-                                   skip the root-to-neighbourhood descent.  Results do not depend on it. */
+                                   skip the root-to-neighbourhood descent.  Results do not depend on it.  Measured (profiles/r02_c3_variants.md):
+                                   node visits per segment 18.7 -> 7.7 on C3 and 9.7 -> 4.9 on C2, throughput +-1 % -- a warp walks until
+                                   its LONGEST ray is done and long rays start at the root either way -- hence off by default. */
     PT_OPT_ENTRY_CELLS_PER_PRIM = 13, /* the finest level has at most this many blocks per primitive (default 2) */
     PT_OPT_SAH_TREELETS = 11    /* 1: the refit passes restructure 7-leaf treelets by dynamic programming instead of
                                    single rotations: lower SAH (C2 11.06 vs 11.24), but 1.5 ms instead of 0.06 ms per

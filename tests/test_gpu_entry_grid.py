@@ -100,6 +100,8 @@ def test_entry_grid_is_off_for_reference_leaf_boxes_and_single_primitives(sky):
     r.close()
     sc = scenes.sphere_field(500, 64, 36)
     r = api.Renderer(sc, sky)
+    assert r.stats()["entry_levels"] == 0                     # off by default
+    r.set_option(api.PT_OPT_ENTRY_GRID, 12); r.build()
     assert r.stats()["entry_levels"] > 0
     r.set_option(api.PT_OPT_REF_LEAF_BOXES, 1); r.build()
     assert r.stats()["entry_levels"] == 0
