@@ -15,6 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpt_b200.so")          # default: uncontracted arithmetic == the CPU oracle's
 LIB_PATH_FMA = os.path.join(_HERE, "libpt_b200_fma.so")  # nvcc-contracted arithmetic == the reference's CUDA build
+LIB_PATH_GRID = os.path.join(_HERE, "libpt_b200_grid.so")  # default arithmetic + the entry-grid code (PT_OPT_ENTRY_GRID)
 
 PT_OPT_WAVE_PATHS, PT_OPT_STAGE_TIMING, PT_OPT_TIE_ORDER, PT_OPT_SKY_QUARTER_ROWS = 1, 2, 3, 4
 PT_OPT_TRAV_INNER_RUN, PT_OPT_COUNT_STEPS, PT_OPT_REF_LEAF_BOXES, PT_OPT_SAH_PASSES, PT_OPT_SAH_TREELETS = 7, 8, 9, 10, 11

@@ -902,9 +902,11 @@ const char* pt_last_error(void) { return g_err.c_str(); }
 int pt_set_error_text(const char* msg) { g_err = msg ? msg : ""; return 0; }   // for the other translation units of the library
 const char* pt_version(void) {
 #ifdef PT_VARIANT_FMA
-    return "cpppathtracer_b200 0.1 (sm_100a wavefront, fma-contracted arithmetic)";
+    return "cpppathtracer_b200 0.2 (sm_100a wavefront, fma-contracted arithmetic)";
+#elif PT_ENTRY_GRID_CODE
+    return "cpppathtracer_b200 0.2 (sm_100a wavefront, entry grid)";
 #else
-    return "cpppathtracer_b200 0.1 (sm_100a wavefront)";
+    return "cpppathtracer_b200 0.2 (sm_100a wavefront)";
 #endif
 }
 
@@ -974,6 +976,9 @@ int pt_set_option(pt_scene* s, int option, int64_t value) {
             s->opt_sah_passes = (int)value; s->dirty = true; return PT_OK;
         case PT_OPT_ENTRY_GRID:
             if (value < 0 || value > 20) return fail(PT_ERR_INVALID, "PT_OPT_ENTRY_GRID: 0 (off) .. 20 levels");
+#if !PT_ENTRY_GRID_CODE
+            if (value != 0) return fail(PT_ERR_INVALID, "this build carries no entry-grid code in its kernels: use libpt_b200_grid.so");
+#endif
             s->opt_entry_grid = (int)value; s->dirty = true; return PT_OK;
         case PT_OPT_ENTRY_CELLS_PER_PRIM:
             if (value < 1 || value > 64) return fail(PT_ERR_INVALID, "PT_OPT_ENTRY_CELLS_PER_PRIM: 1 .. 64");

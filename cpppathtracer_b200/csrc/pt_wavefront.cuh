@@ -30,6 +30,9 @@ namespace pt {
 #ifndef PT_PREFETCH_FAR
 #define PT_PREFETCH_FAR 1
 #endif
+#ifndef PT_ENTRY_GRID_CODE
+#define PT_ENTRY_GRID_CODE 0   // 0: build variant without the entry-grid look-up in the kernels (A/B of its cost when unused)
+#endif
 #ifndef PT_STACK_TOP
 #define PT_STACK_TOP 1
 #endif
@@ -198,6 +201,9 @@ __device__ __forceinline__ void lane_setup(const SceneDev& sc, LaneRay& r, int* 
     r.top = PT_SENTINEL;
 #endif
     r.node = sc.n_tree_prims > 0 ? 0 : PT_SENTINEL;
+#if !PT_ENTRY_GRID_CODE
+    return;
+#endif
     const EntryGrid& g = sc.grid;
     if (g.lmax < 0 || sc.n_tree_prims <= 0) return;
     // ---- the ray as a segment: clipped to the gridded box and to [lo, hi] (tmin .. platform hit), same FMA slabs and

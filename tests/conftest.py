@@ -13,7 +13,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
     # a fresh checkout has no built libraries (they are git-ignored): build them once, like the driver's build()
-    need = [os.path.join(ROOT, "cpppathtracer_b200", "libpt_b200.so"), os.path.join(ROOT, "cpppathtracer_b200", "libpt_b200_fma.so"),
+    need = [os.path.join(ROOT, "cpppathtracer_b200", "libpt_b200.so"), os.path.join(ROOT, "cpppathtracer_b200", "libpt_b200_fma.so"), os.path.join(ROOT, "cpppathtracer_b200", "libpt_b200_grid.so"),
             os.path.join(ROOT, "oracle", "libpt_oracle.so")]
     if not all(os.path.exists(p) for p in need):
         import __graft_entry__ as g

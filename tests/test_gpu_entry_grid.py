@@ -72,7 +72,7 @@ def test_entry_grid_changes_no_hit(name, sky):
     rays = _ray_batch(sc, rng, 6000)
     out = {}
     for levels in (0, 12):
-        r = api.Renderer(sc, sky)
+        r = api.Renderer(sc, sky, lib_path=api.LIB_PATH_GRID)
         r.set_option(api.PT_OPT_ENTRY_GRID, levels); r.set_option(api.PT_OPT_ENTRY_CELLS_PER_PRIM, 8); r.build()
         st = r.stats()
         prim, t, nrm, pos = r.trace(rays)
@@ -95,14 +95,21 @@ def test_entry_grid_changes_no_hit(name, sky):
 
 def test_entry_grid_is_off_for_reference_leaf_boxes_and_single_primitives(sky):
     sc = scenes.sphere_field(1, 64, 36)
-    r = api.Renderer(sc, sky)
+    r = api.Renderer(sc, sky, lib_path=api.LIB_PATH_GRID)
+    r.set_option(api.PT_OPT_ENTRY_GRID, 12); r.build()
     assert r.stats()["entry_levels"] == 0
     r.close()
     sc = scenes.sphere_field(500, 64, 36)
-    r = api.Renderer(sc, sky)
+    r = api.Renderer(sc, sky, lib_path=api.LIB_PATH_GRID)
     assert r.stats()["entry_levels"] == 0                     # off by default
     r.set_option(api.PT_OPT_ENTRY_GRID, 12); r.build()
     assert r.stats()["entry_levels"] > 0
     r.set_option(api.PT_OPT_REF_LEAF_BOXES, 1); r.build()
     assert r.stats()["entry_levels"] == 0
+    r.close()
+    # the default library carries no entry-grid code in its kernels (it costs 4 % on C2 even when unused) and says so
+    r = api.Renderer(sc, sky)
+    with pytest.raises(api.PtError):
+        r.set_option(api.PT_OPT_ENTRY_GRID, 12)
+    r.set_option(api.PT_OPT_ENTRY_GRID, 0)
     r.close()

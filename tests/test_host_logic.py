@@ -20,13 +20,14 @@ def _declared_symbols():
 def test_library_exports_every_declared_symbol():
     names = _declared_symbols()
     assert len(names) >= 25
-    for path in (api.LIB_PATH, api.LIB_PATH_FMA):
+    for path in (api.LIB_PATH, api.LIB_PATH_FMA, api.LIB_PATH_GRID):
         lib = api.load_library(path)
         for n in names:
             assert hasattr(lib, n), f"{path} does not export {n}"
         assert b"sm_100a" in lib.pt_version()
     assert sorted(api.EXPORTS) == names
     assert b"fma" in api.load_library(api.LIB_PATH_FMA).pt_version() and b"fma" not in api.load_library().pt_version()
+    assert b"entry grid" in api.load_library(api.LIB_PATH_GRID).pt_version() and b"entry grid" not in api.load_library().pt_version()
 
 
 def test_no_cpu_fallback_without_device():

@@ -11,7 +11,7 @@ for which in sys.argv[1:] or ["c1", "c2", "c3"]:
     spp = {"c1": 64, "c2": 16, "c3": 8}[which]
     base = None
     for levels, cpp, run in ((0, 2, 4), (12, 2, 4), (12, 8, 4), (12, 32, 4), (12, 8, 2), (12, 8, 3), (12, 8, 6), (0, 2, 3)):
-        r = api.Renderer(sc, sky)
+        r = api.Renderer(sc, sky, lib_path=api.LIB_PATH_GRID)
         r.set_option(api.PT_OPT_ENTRY_GRID, levels); r.set_option(api.PT_OPT_ENTRY_CELLS_PER_PRIM, cpp); r.set_option(api.PT_OPT_TRAV_INNER_RUN, run); r.build()
         b = r.stats()
         for _ in range(3):

@@ -21,6 +21,8 @@ METRICS = [
     ("FMA pipe %", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", 1.0),
     ("ALU pipe %", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", 1.0),
     ("FP64 pipe %", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", 1.0),
+    ("L2 throughput % of peak", "lts__throughput.avg.pct_of_peak_sustained_elapsed", 1.0),
+    ("SM throughput % of peak", "sm__throughput.avg.pct_of_peak_sustained_elapsed", 1.0),
 ]
 UNIT_TO_GB = {"byte": 1e-9, "Kbyte": 1e-6, "Mbyte": 1e-3, "Gbyte": 1.0, "Tbyte": 1e3}
 UNIT_TO_MS = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3, "second": 1e3, "msecond": 1.0, "usecond": 1e-3, "nsecond": 1e-6}
@@ -105,6 +107,8 @@ def sass_regions(rep, launch_index):
 def main():
     rep, out_md = sys.argv[1], sys.argv[2]
     traffic_path = sys.argv[sys.argv.index("--traffic") + 1] if "--traffic" in sys.argv else None
+    wave_paths = int(sys.argv[sys.argv.index("--wave-paths") + 1]) if "--wave-paths" in sys.argv else 1920 * 1080 * 16
+    what = sys.argv[sys.argv.index("--what") + 1] if "--what" in sys.argv else "tools/profile_target.py (C2, 1920x1080, 16 spp = 33.2 M paths, depth 8)"
     L = raw_page(rep)
     if not L:
         sys.exit("no k_bounce launches in " + rep)
@@ -132,11 +136,10 @@ def main():
     if traffic_path:
         per = [(d["DRAM read [GB]"] + d["DRAM write [GB]"]) * 1e9 for d in L]
         json.dump({"kernel": "k_bounce", "dram_bytes_per_launch": sum(per) / n, "per_launch_bytes": per, "launches": n,
-                   "dram_bytes_per_wave": sum(per), "wave_paths": 1920 * 1080 * 16,
+                   "dram_bytes_per_wave": sum(per), "wave_paths": wave_paths,
                    "ipc_time_weighted": sum(d["IPC (of 4)"] * d["duration [ms]"] for d in L) / sum(d["duration [ms]"] for d in L),
                    "lanes_per_instruction_time_weighted": sum(d["lanes / instruction"] * d["duration [ms]"] for d in L) / sum(d["duration [ms]"] for d in L),
-                   "source": f"ncu --set full ({rep}), the {n} k_bounce launches of one wave of tools/profile_target.py (C2, 1920x1080, "
-                             "16 spp = 33.2 M paths, depth 8): dram__bytes_read.sum + dram__bytes_write.sum"},
+                   "source": f"ncu --set full ({rep}), the {n} k_bounce launches of one wave of {what}: dram__bytes_read.sum + dram__bytes_write.sum"},
                   open(traffic_path, "w"), indent=1)
     print("\n".join(lines))
 

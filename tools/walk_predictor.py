@@ -56,7 +56,7 @@ def main():
         cam = copy.deepcopy(sc.camera); cam.width, cam.height = 960, 540
         lo, hi, k = grid_of(sc)
         for grid in (0, 12):
-            r = api.Renderer(sc, sky)
+            r = api.Renderer(sc, sky, lib_path=api.LIB_PATH_GRID)
             r.set_option(api.PT_OPT_ENTRY_GRID, grid); r.set_option(api.PT_OPT_ENTRY_CELLS_PER_PRIM, 8); r.build()
             lmax = r.stats()["entry_levels"] if grid else 9
             r.set_option(api.PT_OPT_COUNT_STEPS, 1)

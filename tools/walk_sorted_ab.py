@@ -21,7 +21,7 @@ for which in sys.argv[1:] or ["c2", "c3"]:
             batch.append(rays[valid])
         rays = np.concatenate(batch)
         for grid in (0, 12):
-            r = api.Renderer(sc, sky)
+            r = api.Renderer(sc, sky, lib_path=api.LIB_PATH_GRID)
             r.set_option(api.PT_OPT_ENTRY_GRID, grid); r.set_option(api.PT_OPT_ENTRY_CELLS_PER_PRIM, 8); r.build()
             lmax = r.stats()["entry_levels"] if grid else 9
             lvl, miss = levels_of(rays, sc, lo, hi, k, lmax)
