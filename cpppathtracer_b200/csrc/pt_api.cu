@@ -59,6 +59,23 @@ struct DeviceGuard {
 };
 #define PT_ON_SCENE_DEVICE(s) DeviceGuard pt_device_guard_((s) ? (s)->device : 0)
 
+// page-locked staging buffer that only grows: the scene description is re-uploaded by every pt_build, and a pageable
+// source makes each cudaMemcpyAsync a synchronous staged copy (3.3 -> 2 ms per rebuild at 128 k primitives)
+template <class T>
+struct PinnedBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t reserve(size_t count) {
+        if (count <= n) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; n = 0;
+        cudaError_t e = cudaHostAlloc((void**)&p, count * sizeof(T), cudaHostAllocDefault);
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; n = 0; }
+};
+
 struct HostPrim {
     int type;
     float c[3];
@@ -109,6 +126,9 @@ struct pt_scene {
     DevBuf<uint32_t> codes, codes_sorted, ids, ids_sorted, bounds6;
     DevBuf<int> orig_id;
     DevBuf<unsigned char> cub_tmp;
+    PinnedBuf<float4> st_g0, st_g1;      // staging of the uploads of pt_build
+    PinnedBuf<int> st_orig, st_tree;
+    DevBuf<float4> nodes4;               // build variant PT_BVH4
     DevBuf<int4> grid_cells;
     DevBuf<uint4> grid_levels;
     EntryGrid grid{nullptr, nullptr, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, 0, -1};
@@ -309,13 +329,10 @@ struct RefOrder {
 // Sizes, uploads and fills the entry grid (struct EntryGrid) for the tree that was just packed.  The gridded box is
 // computed on the host from the primitives (no device round trip): it only has to CONTAIN every leaf box, so it is
 // padded by 2^-10 of the scene's size plus the boxes' own inflation.
-int build_entry_grid(pt_scene* s, const std::vector<int>& tree_prims) {
+int build_entry_grid(pt_scene* s, int nt) {
     s->grid.lmax = -1;
-    const int nt = (int)tree_prims.size();
     if (s->opt_entry_grid <= 0 || s->opt_ref_leaf_boxes || nt < 2) return PT_OK;
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, amax = 0.0;
-    // tree_prims holds DEVICE indices; the host primitives are found through the same rank table the upload used,
-    // so walk the host list and skip platforms instead
     for (const HostPrim& p : s->prims) {
         if (p.type != PT_PRIM_SPHERE && p.type != PT_PRIM_CYLINDER) continue;
         const double ar = std::fabs((double)p.radius);
@@ -388,9 +405,12 @@ int upload_and_build(pt_scene* s) {
             }
         }
     } else for (int i = 0; i < n; ++i) rank[i] = (uint32_t)i;
-    std::vector<float4> g0(std::max(n, 1)), g1(std::max(n, 1));
-    std::vector<int> orig(std::max(n, 1));
-    std::vector<float> py; std::vector<int> pid, tree;
+    const size_t n1 = (size_t)std::max(n, 1);
+    CK(s->st_g0.reserve(n1)); CK(s->st_g1.reserve(n1)); CK(s->st_orig.reserve(n1)); CK(s->st_tree.reserve(n1));
+    CK(cudaStreamSynchronize(st));          // the staging buffers may still feed the previous build's copies
+    float4* const g0 = s->st_g0.p; float4* const g1 = s->st_g1.p; int* const orig = s->st_orig.p;
+    std::vector<float> py; std::vector<int> pid;
+    int* const tree = s->st_tree.p; int n_tree_prims = 0;
     s->has_emitters = 0;
     for (int i = 0; i < n; ++i) {
         const HostPrim& p = s->prims[i];
@@ -407,18 +427,18 @@ int upload_and_build(pt_scene* s) {
     for (int d = 0; d < n; ++d) {
         const HostPrim& p = s->prims[orig[d]];
         if (p.type == PT_PRIM_PLATFORM) { py.push_back(p.y_pos); pid.push_back(d); }
-        else if (p.type == PT_PRIM_SPHERE || p.type == PT_PRIM_CYLINDER) tree.push_back(d);
+        else if (p.type == PT_PRIM_SPHERE || p.type == PT_PRIM_CYLINDER) tree[n_tree_prims++] = d;
     }
     std::vector<MaterialRec> recs(std::max<size_t>(s->materials.size(), 1));
     for (size_t i = 0; i < s->materials.size(); ++i) recs[i] = make_material_rec(s->materials[i]);
 
-    CK(s->geo0.reserve(g0.size())); CK(s->geo1.reserve(g1.size())); CK(s->mats.reserve(recs.size()));
-    CK(s->orig_id.reserve(orig.size()));
+    CK(s->geo0.reserve(n1)); CK(s->geo1.reserve(n1)); CK(s->mats.reserve(recs.size()));
+    CK(s->orig_id.reserve(n1));
     CK(s->plat_y.reserve(std::max<size_t>(py.size(), 1))); CK(s->plat_id.reserve(std::max<size_t>(pid.size(), 1)));
-    CK(cudaMemcpyAsync(s->geo0.p, g0.data(), g0.size() * sizeof(float4), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(s->geo1.p, g1.data(), g1.size() * sizeof(float4), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s->geo0.p, g0, n1 * sizeof(float4), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s->geo1.p, g1, n1 * sizeof(float4), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(s->mats.p, recs.data(), recs.size() * sizeof(MaterialRec), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(s->orig_id.p, orig.data(), orig.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s->orig_id.p, orig, n1 * sizeof(int), cudaMemcpyHostToDevice, st));
     if (!py.empty()) {
         CK(cudaMemcpyAsync(s->plat_y.p, py.data(), py.size() * sizeof(float), cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(s->plat_id.p, pid.data(), pid.size() * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -430,7 +450,7 @@ int upload_and_build(pt_scene* s) {
         CK(cudaMemcpyAsync(s->test_mx.p, tb_mx.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, st));
     }
     s->n_plat = (int)py.size();
-    s->n_tree = (int)tree.size();
+    s->n_tree = n_tree_prims;
     s->grid.lmax = -1; s->grid.cells = nullptr; s->grid.levels = nullptr;
     s->stats.entry_levels = 0; s->stats.entry_cells = 0;
     const int nt = s->n_tree;
@@ -439,11 +459,16 @@ int upload_and_build(pt_scene* s) {
     CK(cudaEventRecord(eb0, st));
     if (nt > 0) {
         CK(s->bvh_prims.reserve(nt));
-        CK(cudaMemcpyAsync(s->bvh_prims.p, tree.data(), nt * sizeof(int), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(s->bvh_prims.p, tree, nt * sizeof(int), cudaMemcpyHostToDevice, st));
         CK(s->nodes.reserve(4 * (size_t)std::max(nt - 1, 1)));
         if (nt == 1) {
             k_lbvh_single<<<1, 1, 0, st>>>(s->bvh_prims.p, s->geo0.p, s->geo1.p, s->nodes.p);
             s->stats.launches += 1;
+#if PT_BVH4
+            CK(s->nodes4.reserve(8));
+            k_lbvh_collapse4<<<1, 32, 0, st>>>(2, s->nodes.p, s->nodes4.p);
+            s->stats.launches += 1;
+#endif
         } else {
             CK(s->leaf_mn.reserve(nt)); CK(s->leaf_mx.reserve(nt)); CK(s->leaf_c.reserve(nt)); CK(s->inner_mn.reserve(nt)); CK(s->inner_mx.reserve(nt));
             CK(s->codes.reserve(nt)); CK(s->codes_sorted.reserve(nt)); CK(s->ids.reserve(nt)); CK(s->ids_sorted.reserve(nt));
@@ -481,7 +506,12 @@ int upload_and_build(pt_scene* s) {
             k_lbvh_pack<<<gb, tb, 0, st>>>(nt, s->ids_sorted.p, s->bvh_prims.p, s->geo1.p, s->leaf_mn.p, s->leaf_mx.p,
                                            s->children.p, s->inner_mn.p, s->inner_mx.p, s->nodes.p);
             s->stats.launches += 5 + 2;   // + the radix sort's own kernels (library), counted as 2
-            int rc = build_entry_grid(s, tree);
+#if PT_BVH4
+            CK(s->nodes4.reserve(8 * (size_t)std::max(nt - 1, 1)));
+            k_lbvh_collapse4<<<gb, tb, 0, st>>>(nt, s->nodes.p, s->nodes4.p);
+            s->stats.launches += 1;
+#endif
+            int rc = build_entry_grid(s, nt);
             if (rc) return rc;
         }
         CK(cudaGetLastError());
@@ -500,7 +530,7 @@ int upload_and_build(pt_scene* s) {
 SceneDev scene_dev(pt_scene* s) {
     SceneDev d;
     d.grid = s->grid;
-    d.nodes = s->nodes.p; d.geo0 = s->geo0.p; d.geo1 = s->geo1.p; d.mats = s->mats.p;
+    d.nodes = s->nodes.p; d.nodes4 = s->nodes4.p; d.geo0 = s->geo0.p; d.geo1 = s->geo1.p; d.mats = s->mats.p;
     d.plat_y = s->plat_y.p; d.plat_id = s->plat_id.p; d.orig_id = s->orig_id.p;
     d.n_plat = s->n_plat; d.n_tree_prims = s->n_tree; d.sky = s->sky.obj; d.has_emitters = s->has_emitters;
     return d;
@@ -947,6 +977,7 @@ void pt_scene_destroy(pt_scene* s) {
     s->orig_id.release(); s->cub_tmp.release(); s->accum.release(); s->read_tmp.release(); s->path_out.release(); s->hit.release();
     s->ctrl.release(); s->q_o.release(); s->q_d.release(); s->seg_counter.release();
     s->node_height.release(); s->sah_dev.release(); s->grid_cells.release(); s->grid_levels.release();
+    s->st_g0.release(); s->st_g1.release(); s->st_orig.release(); s->st_tree.release(); s->nodes4.release();
     for (int k = 0; k < 2; ++k) { s->hq_p[k].release(); s->hq_d[k].release(); s->hq_thr[k].release(); s->scratch_i[k].release(); }
     for (auto& b : s->scratch_f) b.release();
     s->disp_color.release(); s->disp_normal.release(); s->disp_mix.release(); s->disp_depth.release(); s->disp_bgra.release();

@@ -522,6 +522,47 @@ __global__ void k_entry_grid(EntryGridBuild g, const float4* __restrict__ nodes)
     g.cells[cell] = make_int4(f[0], f[1], f[2], f[3]);
 }
 
+// pass 7 (build variant PT_BVH4): 4-wide nodes collapsed from the packed binary tree.  Node4[i] exists for EVERY binary inner node i (no
+// depth pass, no compaction: a walk that starts at the root only ever reaches the even-depth ones): each child of i that is an inner node
+// is replaced by its own two children, a leaf child stays.  128 bytes, component-major so that the four slab tests vectorise:
+//   q0 = cx[4]  q1 = cy[4]  q2 = cz[4]  q3 = hx[4]  q4 = hy[4]  q5 = hz[4]  q6 = links[4]  (q7 unused)
+// an unused slot has half-extent -1 (never hit) and link 0x7fffffff.
+__global__ void k_lbvh_collapse4(int n, const float4* __restrict__ nodes, float4* __restrict__ nodes4) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    float c[3][4], h[3][4]; int link[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { c[0][k] = c[1][k] = c[2][k] = 0.f; h[0][k] = h[1][k] = h[2][k] = -1.f; link[k] = 0x7fffffff; }
+    int m = 0;
+    auto put = [&](float cx, float cy, float cz, float hx, float hy, float hz, int l) {
+        c[0][m] = cx; c[1][m] = cy; c[2][m] = cz; h[0][m] = hx; h[1][m] = hy; h[2][m] = hz; link[m] = l; ++m;
+    };
+    auto take = [&](const float4* p, int which, bool expand) {
+        const float4 n0 = p[0], n1 = p[1], n2 = p[2], n3 = p[3];
+        const int l = __float_as_int(which == 0 ? n3.x : n3.y);
+        if (expand && l >= 0) return l;                       // caller descends into this inner child
+        if (which == 0) put(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, l);
+        else put(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, l);
+        return -1;
+    };
+    const float4* p = nodes + 4 * (size_t)i;
+    for (int which = 0; which < 2; ++which) {
+        const int inner = take(p, which, true);
+        if (inner >= 0) {
+            const float4* q = nodes + 4 * (size_t)inner;
+            // a never-entered second child (single-primitive tree) has a negative half-extent and stays out
+            take(q, 0, false);
+            take(q, 1, false);
+        }
+    }
+    float4* o = nodes4 + 8 * (size_t)i;
+    o[0] = make_float4(c[0][0], c[0][1], c[0][2], c[0][3]); o[1] = make_float4(c[1][0], c[1][1], c[1][2], c[1][3]);
+    o[2] = make_float4(c[2][0], c[2][1], c[2][2], c[2][3]); o[3] = make_float4(h[0][0], h[0][1], h[0][2], h[0][3]);
+    o[4] = make_float4(h[1][0], h[1][1], h[1][2], h[1][3]); o[5] = make_float4(h[2][0], h[2][1], h[2][2], h[2][3]);
+    o[6] = make_float4(__int_as_float(link[0]), __int_as_float(link[1]), __int_as_float(link[2]), __int_as_float(link[3]));
+    o[7] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 // a tree over a single primitive: one node whose second child can never be entered
 __global__ void k_lbvh_single(const int* __restrict__ bvh_prims, const float4* __restrict__ geo0,
                               const float4* __restrict__ geo1, float4* __restrict__ nodes) {

@@ -33,6 +33,9 @@ namespace pt {
 #ifndef PT_ENTRY_GRID_CODE
 #define PT_ENTRY_GRID_CODE 0   // 0: build variant without the entry-grid look-up in the kernels (A/B of its cost when unused)
 #endif
+#ifndef PT_BVH4
+#define PT_BVH4 0             // 1: build variant that walks 4-wide nodes collapsed from the binary tree
+#endif
 #ifndef PT_STACK_TOP
 #define PT_STACK_TOP 1
 #endif
@@ -73,6 +76,7 @@ struct EntryGrid {
 struct SceneDev {
     EntryGrid grid;
     const float4* nodes;      // LBVH, 4 x float4 per inner node
+    const float4* nodes4;     // build variant PT_BVH4: 8 x float4 per inner node (k_lbvh_collapse4)
     const float4* geo0;       // (cx, cy, cz, radius)
     const float4* geo1;       // (height, y_pos, bits type, bits (bin<<28 | material slot))
     const MaterialRec* mats;
@@ -294,6 +298,49 @@ __device__ __forceinline__ void lane_inner(const SceneDev& sc, LaneRay& r, int* 
         else r.node = stack_pop(r, stack);
     }
 }
+#if PT_BVH4
+// 4-wide visit (build variant, profiles/r02_c3_variants.md): four slab tests on one 128-byte node, the hits sorted by entry
+// distance together with their links (5 compare-exchanges), nearest next, the others pushed far-to-near.
+__device__ __forceinline__ void cmpx(float& ka, int& la, float& kb, int& lb) {
+    const bool sw = kb < ka;
+    const float k0 = sw ? kb : ka, k1 = sw ? ka : kb;
+    const int l0 = sw ? lb : la, l1 = sw ? la : lb;
+    ka = k0; kb = k1; la = l0; lb = l1;
+}
+__device__ __forceinline__ void lane_inner4(const SceneDev& sc, LaneRay& r, int* stack) {
+    const float4* p = sc.nodes4 + 8 * (size_t)r.node;
+    float4 cx, cy, cz, hx, hy, hz, lk, pad;
+    load_node(p, 0, cx, cy, cz, hx);
+    load_node(p + 4, 0, hy, hz, lk, pad);
+    const float ax = fabsf(r.ix), ay = fabsf(r.iy), az = fabsf(r.iz);
+    const float lo = r.lo, hi = r.hi;
+    const float BIG = 3.0e38f;
+    float e[4]; int l[4];
+    const float c_x[4] = {cx.x, cx.y, cx.z, cx.w}, c_y[4] = {cy.x, cy.y, cy.z, cy.w}, c_z[4] = {cz.x, cz.y, cz.z, cz.w};
+    const float h_x[4] = {hx.x, hx.y, hx.z, hx.w}, h_y[4] = {hy.x, hy.y, hy.z, hy.w}, h_z[4] = {hz.x, hz.y, hz.z, hz.w};
+    const float lks[4] = {lk.x, lk.y, lk.z, lk.w};
+    int n = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float tx = fmaf(c_x[k], r.ix, -r.ox), ty = fmaf(c_y[k], r.iy, -r.oy), tz = fmaf(c_z[k], r.iz, -r.oz);
+        const float en = fmaxf(fmaxf(fmaf(-h_x[k], ax, tx), fmaf(-h_y[k], ay, ty)), fmaxf(fmaf(-h_z[k], az, tz), lo));
+        const float ex = fminf(fminf(fmaf(h_x[k], ax, tx), fmaf(h_y[k], ay, ty)), fminf(fmaf(h_z[k], az, tz), hi));
+        const bool hit = en <= ex;
+        e[k] = hit ? en : BIG;
+        l[k] = __float_as_int(lks[k]);
+        n += hit ? 1 : 0;
+    }
+    cmpx(e[0], l[0], e[1], l[1]); cmpx(e[2], l[2], e[3], l[3]);
+    cmpx(e[0], l[0], e[2], l[2]); cmpx(e[1], l[1], e[3], l[3]);
+    cmpx(e[1], l[1], e[2], l[2]);
+    if (n == 0) { r.node = stack_pop(r, stack); return; }
+    if (n > 3) stack_push(r, stack, l[3]);
+    if (n > 2) stack_push(r, stack, l[2]);
+    if (n > 1) stack_push(r, stack, l[1]);
+    r.node = l[0];
+}
+#endif
+
 __device__ __forceinline__ void lane_leaf_test(const SceneDev& sc, LaneRay& r, int code) {
     const uint32_t leaf = (uint32_t)~code;
     const uint32_t prim = leaf >> 2;
@@ -547,7 +594,11 @@ __global__ void PT_BOUNCE_BOUNDS k_bounce(const BounceArgs a) {
                 if (alive) {
                     int k = 0;
 #pragma unroll 1
+#if PT_BVH4
+                    while (r.node >= 0 && r.node != PT_SENTINEL && k < a.inner_run) { lane_inner4(sc, r, stack); ++k; if (COUNT_STEPS) { ++n_inner; ++lane_steps; } }
+#else
                     while (r.node >= 0 && r.node != PT_SENTINEL && k < a.inner_run) { lane_inner(sc, r, stack); ++k; if (COUNT_STEPS) { ++n_inner; ++lane_steps; } }
+#endif
                 }
                 if (alive && r.node < 0) { lane_leaf(sc, r, stack); if (COUNT_STEPS) { ++n_leaf; ++lane_steps; } }
             }
