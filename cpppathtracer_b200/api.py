@@ -47,7 +47,7 @@ EXPORTS = [
     "pt_add_cylinder", "pt_set_material", "pt_update_prim", "pt_set_sky_rgba8", "pt_build", "pt_render_frame",
     "pt_render_frame_async", "pt_synchronize", "pt_reset_accum", "pt_ensure_frame", "pt_read_accum", "pt_accum_device_ptr",
     "pt_get_stats", "pt_dispatch_ray", "pt_dispatch_ray_frame", "pt_dispatch_ray_begin", "pt_dispatch_ray_end", "pt_texture_create_rgba8", "pt_texture_destroy", "pt_trace_rays", "pt_last_trace_steps",
-    "pt_shade_batch", "pt_raygen_batch", "pt_sky_lookup", "pt_philox_uniforms", "pt_camera_basis", "pt_camera_control",
+    "pt_shade_batch", "pt_raygen_batch", "pt_sky_lookup", "pt_philox_uniforms", "pt_sort_code_pairs", "pt_camera_basis", "pt_camera_control",
     "pt_last_error",
     "pt_version", "pt_image_load_png", "pt_image_free",
 ]
@@ -94,6 +94,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.pt_raygen_batch.argtypes = [C.c_void_p, C.POINTER(PtCamera), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.pt_sky_lookup.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.pt_philox_uniforms.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]
+    lib.pt_sort_code_pairs.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.pt_camera_basis.argtypes = [C.POINTER(PtCamera), C.c_void_p]
     lib.pt_camera_control.argtypes = [C.POINTER(PtCamera), C.c_int, C.c_float, C.c_float]
     lib.pt_accum_device_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
@@ -352,6 +353,13 @@ class Renderer:
         out = np.empty_like(dirs)
         self._check(self.lib.pt_sky_lookup(self.h, dirs.shape[0], dirs.ctypes.data, out.ctypes.data))
         return out
+
+    def sort_code_pairs(self, codes: np.ndarray):
+        """The LBVH build's radix sort on caller-supplied codes: (codes_sorted, input positions), stable."""
+        codes = np.ascontiguousarray(codes, np.uint32)
+        ks = np.empty_like(codes); vs = np.empty_like(codes)
+        self._check(self.lib.pt_sort_code_pairs(self.h, codes.shape[0], codes.ctypes.data, ks.ctypes.data, vs.ctypes.data))
+        return ks, vs
 
     def philox(self, seed: int, pixel_sample_slot: np.ndarray) -> np.ndarray:
         pss = np.ascontiguousarray(pixel_sample_slot, np.uint32)

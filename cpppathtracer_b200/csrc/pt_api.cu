@@ -103,6 +103,10 @@ struct pt_scene {
     bool dirty = true, built = false;
     std::vector<uint32_t> rank_cache;        // reference leaf rank per primitive, from the last build after an add
     bool rank_valid = false;
+    bool layout_valid = false;               // staging buffers + device index lists match the primitive list and its order
+    size_t st_n = 0;
+    std::vector<int> moved;                  // primitives edited by pt_update_prim since the last build
+    std::vector<float> plat_y_host; std::vector<int> plat_ids_host;
     // options
     uint32_t opt_wave_paths = 128u << 20;  // 64 spp per wave at 1080p: 26 GB of hit queues; 5.57 vs 5.40 Gpaths/s with 32 Mi (16 spp), 5.23 with 16 Mi
                                            // (profiles/ab/wave_sweep_v9.log); ensure_queues halves the wave until the queues fit in free memory
@@ -111,7 +115,7 @@ struct pt_scene {
     int opt_sky_quarter = 1;
     int opt_count_steps = 0;
     int opt_ref_leaf_boxes = 0;
-    int opt_inner_run = 4;
+    int opt_inner_run = 6;         // r02 sweep on one box (profiles/ab/r2_inner_run.log): 6 is +0.8 % on C2 and +1.5 % on C3 over 4, -0.6 % on C1
     int opt_sah_treelets = 0;      // 1: the refit passes restructure 7-leaf treelets by dynamic programming (slower build, lower SAH)
     int opt_sah_passes = 4;        // SAH refit passes (tree rotations) after the Karras build; 0: plain LBVH
     int opt_entry_grid = 0;        // finest level the entry grid may use (0, the default: no grid, every walk starts at the root;
@@ -125,7 +129,7 @@ struct pt_scene {
     DevBuf<int2> children;
     DevBuf<uint32_t> codes, codes_sorted, ids, ids_sorted, bounds6;
     DevBuf<int> orig_id;
-    DevBuf<unsigned char> cub_tmp;
+    DevBuf<uint32_t> sort_hist;
     PinnedBuf<float4> st_g0, st_g1;      // staging of the uploads of pt_build
     PinnedBuf<int> st_orig, st_tree;
     DevBuf<float4> nodes4;               // build variant PT_BVH4
@@ -380,6 +384,31 @@ int build_entry_grid(pt_scene* s, int nt) {
     return PT_OK;
 }
 
+// Stable LSD radix sort of the (Morton code, leaf slot) pairs in codes / ids (ids = 0..n-1), 8 bits per pass (pt_lbvh.cuh); the result
+// lands in codes_sorted / ids_sorted.  All four buffers must hold n entries.
+int sort_code_pairs(pt_scene* s, int n) {
+    cudaStream_t st = s->stream;
+    if (n <= PT_SORT_SMALL) {
+        k_sort_small<<<1, 256, 0, st>>>(n, s->codes.p, s->codes_sorted.p, s->ids_sorted.p);
+        s->stats.launches += 1;
+    } else {
+        const int tiles = (n + PT_SORT_TILE - 1) / PT_SORT_TILE;
+        CK(s->sort_hist.reserve((size_t)256 * tiles));
+        uint32_t* kin = s->codes.p; uint32_t* vin = s->ids.p; uint32_t* kout = s->codes_sorted.p; uint32_t* vout = s->ids_sorted.p;
+        for (int shift = 0; shift < 32; shift += 8) {
+            k_sort_hist<<<tiles, 256, 0, st>>>(n, shift, kin, s->sort_hist.p);
+            k_sort_scan<<<1, 1024, 0, st>>>(256 * tiles, s->sort_hist.p);
+            k_sort_scatter<<<tiles, 256, 0, st>>>(n, shift, kin, vin, s->sort_hist.p, kout, vout);
+            std::swap(kin, kout); std::swap(vin, vout);
+        }
+        // four passes: the pairs are back in the buffers they started from -- which now ARE the sorted ones
+        std::swap(s->codes, s->codes_sorted); std::swap(s->ids, s->ids_sorted);
+        s->stats.launches += 12;
+    }
+    CK(cudaGetLastError());
+    return PT_OK;
+}
+
 int upload_and_build(pt_scene* s) {
     const int n = (int)s->prims.size();
     cudaStream_t st = s->stream;
@@ -409,10 +438,8 @@ int upload_and_build(pt_scene* s) {
     CK(s->st_g0.reserve(n1)); CK(s->st_g1.reserve(n1)); CK(s->st_orig.reserve(n1)); CK(s->st_tree.reserve(n1));
     CK(cudaStreamSynchronize(st));          // the staging buffers may still feed the previous build's copies
     float4* const g0 = s->st_g0.p; float4* const g1 = s->st_g1.p; int* const orig = s->st_orig.p;
-    std::vector<float> py; std::vector<int> pid;
-    int* const tree = s->st_tree.p; int n_tree_prims = 0;
-    s->has_emitters = 0;
-    for (int i = 0; i < n; ++i) {
+    int* const tree = s->st_tree.p;
+    auto stage_prim = [&](int i) {
         const HostPrim& p = s->prims[i];
         const pt_material& m = s->materials[p.mat_slot];
         if (m.emit_intensity != 0.f) s->has_emitters = 1;
@@ -423,25 +450,43 @@ int upload_and_build(pt_scene* s) {
         g0[d] = make_float4(p.c[0], p.c[1], p.c[2], p.radius);
         g1[d] = make_float4(p.height, p.y_pos, tf, wf);
         orig[d] = i;
+    };
+    // After updates only (pt_update_prim: no add, no material change, same order) the staging buffers and the index
+    // lists on the device are those of the last build: restage the moved primitives, re-upload the two geometry arrays.
+    const bool moved_only = s->layout_valid && (int)s->st_n == n;
+    if (moved_only) {
+        for (int i : s->moved) stage_prim(i);
+        for (size_t k = 0; k < s->plat_ids_host.size(); ++k) s->plat_y_host[k] = s->prims[orig[s->plat_ids_host[k]]].y_pos;
+    } else {
+        s->has_emitters = 0;
+        for (int i = 0; i < n; ++i) stage_prim(i);
+        s->plat_y_host.clear(); s->plat_ids_host.clear();
+        int n_tree_prims = 0;
+        for (int d = 0; d < n; ++d) {
+            const HostPrim& p = s->prims[orig[d]];
+            if (p.type == PT_PRIM_PLATFORM) { s->plat_y_host.push_back(p.y_pos); s->plat_ids_host.push_back(d); }
+            else if (p.type == PT_PRIM_SPHERE || p.type == PT_PRIM_CYLINDER) tree[n_tree_prims++] = d;
+        }
+        s->n_tree = n_tree_prims;
+        s->st_n = (size_t)n;
     }
-    for (int d = 0; d < n; ++d) {
-        const HostPrim& p = s->prims[orig[d]];
-        if (p.type == PT_PRIM_PLATFORM) { py.push_back(p.y_pos); pid.push_back(d); }
-        else if (p.type == PT_PRIM_SPHERE || p.type == PT_PRIM_CYLINDER) tree[n_tree_prims++] = d;
-    }
-    std::vector<MaterialRec> recs(std::max<size_t>(s->materials.size(), 1));
-    for (size_t i = 0; i < s->materials.size(); ++i) recs[i] = make_material_rec(s->materials[i]);
+    s->moved.clear();
+    const std::vector<float>& py = s->plat_y_host; const std::vector<int>& pid = s->plat_ids_host;
 
-    CK(s->geo0.reserve(n1)); CK(s->geo1.reserve(n1)); CK(s->mats.reserve(recs.size()));
+    CK(s->geo0.reserve(n1)); CK(s->geo1.reserve(n1));
     CK(s->orig_id.reserve(n1));
     CK(s->plat_y.reserve(std::max<size_t>(py.size(), 1))); CK(s->plat_id.reserve(std::max<size_t>(pid.size(), 1)));
     CK(cudaMemcpyAsync(s->geo0.p, g0, n1 * sizeof(float4), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(s->geo1.p, g1, n1 * sizeof(float4), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(s->mats.p, recs.data(), recs.size() * sizeof(MaterialRec), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(s->orig_id.p, orig, n1 * sizeof(int), cudaMemcpyHostToDevice, st));
-    if (!py.empty()) {
-        CK(cudaMemcpyAsync(s->plat_y.p, py.data(), py.size() * sizeof(float), cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(s->plat_id.p, pid.data(), pid.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    if (!py.empty()) CK(cudaMemcpyAsync(s->plat_y.p, py.data(), py.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    std::vector<MaterialRec> recs;
+    if (!moved_only) {
+        recs.resize(std::max<size_t>(s->materials.size(), 1));
+        for (size_t i = 0; i < s->materials.size(); ++i) recs[i] = make_material_rec(s->materials[i]);
+        CK(s->mats.reserve(recs.size()));
+        CK(cudaMemcpyAsync(s->mats.p, recs.data(), recs.size() * sizeof(MaterialRec), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(s->orig_id.p, orig, n1 * sizeof(int), cudaMemcpyHostToDevice, st));
+        if (!pid.empty()) CK(cudaMemcpyAsync(s->plat_id.p, pid.data(), pid.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     }
     const bool use_tb = !tb_mn.empty();
     if (use_tb) {
@@ -450,7 +495,6 @@ int upload_and_build(pt_scene* s) {
         CK(cudaMemcpyAsync(s->test_mx.p, tb_mx.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, st));
     }
     s->n_plat = (int)py.size();
-    s->n_tree = n_tree_prims;
     s->grid.lmax = -1; s->grid.cells = nullptr; s->grid.levels = nullptr;
     s->stats.entry_levels = 0; s->stats.entry_cells = 0;
     const int nt = s->n_tree;
@@ -459,7 +503,7 @@ int upload_and_build(pt_scene* s) {
     CK(cudaEventRecord(eb0, st));
     if (nt > 0) {
         CK(s->bvh_prims.reserve(nt));
-        CK(cudaMemcpyAsync(s->bvh_prims.p, tree, nt * sizeof(int), cudaMemcpyHostToDevice, st));
+        if (!moved_only) CK(cudaMemcpyAsync(s->bvh_prims.p, tree, nt * sizeof(int), cudaMemcpyHostToDevice, st));
         CK(s->nodes.reserve(4 * (size_t)std::max(nt - 1, 1)));
         if (nt == 1) {
             k_lbvh_single<<<1, 1, 0, st>>>(s->bvh_prims.p, s->geo0.p, s->geo1.p, s->nodes.p);
@@ -481,10 +525,7 @@ int upload_and_build(pt_scene* s) {
             k_lbvh_bounds<<<gb, tb, 0, st>>>(nt, s->bvh_prims.p, s->geo0.p, s->geo1.p, use_tb ? s->test_mn.p : nullptr,
                                              use_tb ? s->test_mx.p : nullptr, s->leaf_mn.p, s->leaf_mx.p, s->leaf_c.p, s->bounds6.p);
             k_lbvh_morton<<<gb, tb, 0, st>>>(nt, s->leaf_c.p, s->bounds6.p, s->codes.p, s->ids.p);
-            size_t tmp_bytes = 0;
-            CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, s->codes.p, s->codes_sorted.p, s->ids.p, s->ids_sorted.p, nt, 0, 30, st));
-            CK(s->cub_tmp.reserve(tmp_bytes + 16));
-            CK(cub::DeviceRadixSort::SortPairs(s->cub_tmp.p, tmp_bytes, s->codes.p, s->codes_sorted.p, s->ids.p, s->ids_sorted.p, nt, 0, 30, st));
+            { int rc = sort_code_pairs(s, nt); if (rc) return rc; }
             k_lbvh_hierarchy<<<gb, tb, 0, st>>>(nt, s->codes_sorted.p, s->children.p, s->parent_inner.p, s->parent_leaf.p);
             CK(s->node_height.reserve(nt));
             LbvhTree lt;
@@ -505,7 +546,7 @@ int upload_and_build(pt_scene* s) {
             s->stats.launches += (uint64_t)s->opt_sah_passes + 2;
             k_lbvh_pack<<<gb, tb, 0, st>>>(nt, s->ids_sorted.p, s->bvh_prims.p, s->geo1.p, s->leaf_mn.p, s->leaf_mx.p,
                                            s->children.p, s->inner_mn.p, s->inner_mx.p, s->nodes.p);
-            s->stats.launches += 5 + 2;   // + the radix sort's own kernels (library), counted as 2
+            s->stats.launches += 5;
 #if PT_BVH4
             CK(s->nodes4.reserve(8 * (size_t)std::max(nt - 1, 1)));
             k_lbvh_collapse4<<<gb, tb, 0, st>>>(nt, s->nodes.p, s->nodes4.p);
@@ -524,6 +565,7 @@ int upload_and_build(pt_scene* s) {
     s->stats.bvh_sah_lbvh = nt > 1 ? s->sah_host[0] : 0.f;
     s->stats.bvh_sah = nt > 1 ? (s->opt_sah_passes > 0 ? s->sah_host[1] : s->sah_host[0]) : 0.f;
     s->dirty = false; s->built = true;
+    s->layout_valid = !use_tb;          // (PT_OPT_REF_LEAF_BOXES recomputes everything on every build)
     return PT_OK;
 }
 
@@ -974,7 +1016,7 @@ void pt_scene_destroy(pt_scene* s) {
     s->inner_mn.release(); s->inner_mx.release(); s->mats.release(); s->plat_y.release(); s->plat_id.release();
     s->bvh_prims.release(); s->parent_inner.release(); s->parent_leaf.release(); s->flags.release(); s->children.release();
     s->codes.release(); s->codes_sorted.release(); s->ids.release(); s->ids_sorted.release(); s->bounds6.release();
-    s->orig_id.release(); s->cub_tmp.release(); s->accum.release(); s->read_tmp.release(); s->path_out.release(); s->hit.release();
+    s->orig_id.release(); s->sort_hist.release(); s->accum.release(); s->read_tmp.release(); s->path_out.release(); s->hit.release();
     s->ctrl.release(); s->q_o.release(); s->q_d.release(); s->seg_counter.release();
     s->node_height.release(); s->sah_dev.release(); s->grid_cells.release(); s->grid_levels.release();
     s->st_g0.release(); s->st_g1.release(); s->st_orig.release(); s->st_tree.release(); s->nodes4.release();
@@ -997,10 +1039,10 @@ int pt_set_option(pt_scene* s, int option, int64_t value) {
             if (value < 1024 || value > (1ll << 28)) return fail(PT_ERR_INVALID, "wave_paths out of range");
             s->opt_wave_paths = (uint32_t)value; return PT_OK;
         case PT_OPT_STAGE_TIMING: s->opt_stage_timing = value != 0; return PT_OK;
-        case PT_OPT_TIE_ORDER: s->opt_tie_order = value != 0; s->dirty = true; s->rank_valid = false; return PT_OK;
+        case PT_OPT_TIE_ORDER: s->opt_tie_order = value != 0; s->dirty = true; s->rank_valid = false; s->layout_valid = false; return PT_OK;
         case PT_OPT_SKY_QUARTER_ROWS: s->opt_sky_quarter = value != 0; return PT_OK;
         case PT_OPT_COUNT_STEPS: s->opt_count_steps = value != 0; return PT_OK;
-        case PT_OPT_REF_LEAF_BOXES: s->opt_ref_leaf_boxes = value != 0; s->dirty = true; s->rank_valid = false; return PT_OK;
+        case PT_OPT_REF_LEAF_BOXES: s->opt_ref_leaf_boxes = value != 0; s->dirty = true; s->rank_valid = false; s->layout_valid = false; return PT_OK;
         case PT_OPT_SAH_TREELETS: s->opt_sah_treelets = value != 0; s->dirty = true; return PT_OK;
         case PT_OPT_SAH_PASSES:
             if (value < 0 || value > 16) return fail(PT_ERR_INVALID, "PT_OPT_SAH_PASSES: 0 .. 16");
@@ -1037,7 +1079,7 @@ static int add_prim(pt_scene* s, int type, const float* c, float radius, float y
     pt_material zero; memset(&zero, 0, sizeof(zero));   // the caller memsets Object to 0 (video_renderer.cpp:75,85)
     p.mat_slot = material_slot(s, zero);
     s->prims.push_back(p);
-    s->dirty = true; s->rank_valid = false;
+    s->dirty = true; s->rank_valid = false; s->layout_valid = false;
     return (int)s->prims.size() - 1;
 }
 int pt_add_sphere(pt_scene* s, const float center[3], float radius) {
@@ -1053,7 +1095,7 @@ int pt_set_material(pt_scene* s, int prim, const pt_material* m) {
     if (!s || !m) return fail(PT_ERR_INVALID, "null argument");
     if (prim < 0 || prim >= (int)s->prims.size()) return fail(PT_ERR_INVALID, "primitive id out of range");
     s->prims[prim].mat_slot = material_slot(s, *m);
-    s->dirty = true;
+    s->dirty = true; s->layout_valid = false;
     return PT_OK;
 }
 int pt_update_prim(pt_scene* s, int prim, const float center[3], float radius, float y_pos, float height) {
@@ -1062,7 +1104,7 @@ int pt_update_prim(pt_scene* s, int prim, const float center[3], float radius, f
     HostPrim& p = s->prims[prim];
     if (center) { p.c[0] = center[0]; p.c[1] = center[1]; p.c[2] = center[2]; }
     p.radius = radius; p.y_pos = y_pos; p.height = height;
-    s->dirty = true;
+    s->dirty = true; s->moved.push_back(prim);
     return PT_OK;
 }
 
@@ -1300,6 +1342,24 @@ int pt_philox_uniforms(pt_scene* s, int n, uint64_t seed, const uint32_t* pss, f
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     d.release();
     CK(e);
+    return PT_OK;
+}
+
+int pt_sort_code_pairs(pt_scene* s, int n, const uint32_t* codes, uint32_t* codes_sorted, uint32_t* slots_sorted) {
+    PT_ON_SCENE_DEVICE(s);
+    if (!s || !codes || n < 0) return fail(PT_ERR_INVALID, "bad argument");
+    if (n == 0) return PT_OK;
+    cudaStream_t st = s->stream;
+    CK(s->codes.reserve(n)); CK(s->codes_sorted.reserve(n)); CK(s->ids.reserve(n)); CK(s->ids_sorted.reserve(n));
+    std::vector<uint32_t> iota((size_t)n);
+    for (int i = 0; i < n; ++i) iota[i] = (uint32_t)i;
+    CK(cudaMemcpyAsync(s->codes.p, codes, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s->ids.p, iota.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    int rc = sort_code_pairs(s, n); if (rc) return rc;
+    if (codes_sorted) CK(cudaMemcpyAsync(codes_sorted, s->codes_sorted.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    if (slots_sorted) CK(cudaMemcpyAsync(slots_sorted, s->ids_sorted.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    s->dirty = true;          // the build's scratch buffers were used
     return PT_OK;
 }
 

@@ -1,4 +1,4 @@
-// pt_lbvh.cuh -- GPU LBVH build (Morton codes -> radix sort -> Karras 2012 hierarchy -> bottom-up
+// pt_lbvh.cuh -- GPU LBVH build (Morton codes -> radix sort (own) -> Karras 2012 hierarchy -> bottom-up
 // fit) over the compact SoA primitive records.  Replaces the reference's host-side recursive
 // median-split build with a std::sort per level (SceneBVH::Divide, cuSrc/bvh.cu:31-90; 0.66 s for
 // 100 k objects) and its 112-byte AoS nodes that embed a copy of the Object (include/bvh.h:32-38).
@@ -12,7 +12,6 @@
 // h is rounded up by 4 ulp of (|c| + h) so that [c-h, c+h] contains the box after every rounding of the FMAs.
 // Platforms (infinite AABB, object.cu:141-142,160-161) are kept out of the tree in a side list.
 #pragma once
-#include <cub/cub.cuh>
 #include "pt_math.cuh"
 
 namespace pt {
@@ -130,6 +129,113 @@ __global__ void k_lbvh_morton(int n, const float4* __restrict__ leaf_c, const ui
     uint32_t zi = (uint32_t)fminf(fmaxf(z * 1024.f, 0.f), 1023.f);
     codes[i] = (expand_bits10(xi) << 2) | (expand_bits10(yi) << 1) | expand_bits10(zi);
     ids[i] = (uint32_t)i;
+}
+
+// ---- radix sort of the (Morton code, leaf slot) pairs: 30-bit keys, least-significant digit first, 8 bits per pass, stable ----
+// Round 1 called cub::DeviceRadixSort here, the only library kernel on the path.  Two hand-written paths:
+//   n <= PT_SORT_SMALL : ONE block sorts keys and values entirely in shared memory, four passes, one launch (every scene of
+//                        C1 / C2 / C5 size: the sort is then a single 10-us launch of the per-frame rebuild);
+//   larger             : per pass  k_sort_hist (per-tile digit histogram)  ->  k_sort_scan (exclusive scan, digit-major)  ->
+//                        k_sort_scatter (stable ranks inside the tile by warp match + warp / round prefixes in shared memory).
+// A tile is 256 threads x PT_SORT_ITEMS keys; element e of a tile is handled in round e / 256 by thread e % 256, so "earlier round,
+// lower warp, lower lane" is input order and the scatter is stable.
+#define PT_SORT_SMALL 2048
+#define PT_SORT_ITEMS 8
+#define PT_SORT_TILE (256 * PT_SORT_ITEMS)
+
+// rank of this thread's digit among the threads of the block that hold the same digit and come before it, and the block's
+// count per digit (in cnt[256], valid after the call); `valid` threads only.  Uses warp_hist[8][256].
+__device__ __forceinline__ uint32_t block_digit_rank(uint32_t digit, bool valid, uint32_t (*warp_hist)[256], uint32_t* cnt) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (uint32_t i = threadIdx.x; i < 8u * 256u; i += 256u) (&warp_hist[0][0])[i] = 0u;
+    __syncthreads();
+    // peers = lanes of this warp with the same digit (invalid lanes get a digit of their own: 256 + lane never matches)
+    const uint32_t peers = __match_any_sync(0xffffffffu, valid ? digit : 256u + lane);
+    const uint32_t rank_in_warp = __popc(peers & ((1u << lane) - 1u));
+    if (valid && rank_in_warp == 0u) warp_hist[warp][digit] = __popc(peers);
+    __syncthreads();
+    // thread d turns column d into exclusive prefixes over the warps and leaves the total in cnt[d]
+    uint32_t run = 0u;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { const uint32_t c = warp_hist[w][threadIdx.x]; warp_hist[w][threadIdx.x] = run; run += c; }
+    cnt[threadIdx.x] = run;
+    __syncthreads();
+    return valid ? warp_hist[warp][digit] + rank_in_warp : 0u;
+}
+
+__global__ void __launch_bounds__(256) k_sort_small(int n, const uint32_t* __restrict__ keys_in, uint32_t* __restrict__ keys_out,
+                                                    uint32_t* __restrict__ vals_out) {
+    // values are the identity 0..n-1 on input (k_lbvh_morton), so only the keys are read
+    __shared__ uint32_t k[2][PT_SORT_SMALL], v[2][PT_SORT_SMALL];
+    __shared__ uint32_t warp_hist[8][256], cnt[256], base[256], seen[256];
+    for (int i = threadIdx.x; i < n; i += 256) { k[0][i] = keys_in[i]; v[0][i] = (uint32_t)i; }
+    __syncthreads();
+    int cur = 0;
+    for (int shift = 0; shift < 32; shift += 8) {
+        // digit totals of the whole array, then their exclusive scan
+        cnt[threadIdx.x] = 0u; seen[threadIdx.x] = 0u;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += 256) atomicAdd(&cnt[(k[cur][i] >> shift) & 255u], 1u);
+        __syncthreads();
+        if (threadIdx.x == 0) { uint32_t run = 0u; for (int d = 0; d < 256; ++d) { base[d] = run; run += cnt[d]; } }
+        __syncthreads();
+        for (int i0 = 0; i0 < n; i0 += 256) {
+            const int i = i0 + (int)threadIdx.x;
+            const bool valid = i < n;
+            const uint32_t key = valid ? k[cur][i] : 0u, val = valid ? v[cur][i] : 0u, digit = (key >> shift) & 255u;
+            const uint32_t r = block_digit_rank(digit, valid, warp_hist, cnt);
+            if (valid) { const uint32_t pos = base[digit] + seen[digit] + r; k[cur ^ 1][pos] = key; v[cur ^ 1][pos] = val; }
+            __syncthreads();
+            seen[threadIdx.x] += cnt[threadIdx.x];
+            __syncthreads();
+        }
+        cur ^= 1;
+    }
+    for (int i = threadIdx.x; i < n; i += 256) { keys_out[i] = k[cur][i]; vals_out[i] = v[cur][i]; }
+}
+
+// hist[digit * tiles + tile] = keys of the tile with that digit
+__global__ void __launch_bounds__(256) k_sort_hist(int n, int shift, const uint32_t* __restrict__ keys, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t cnt[256];
+    cnt[threadIdx.x] = 0u;
+    __syncthreads();
+    const int tile0 = blockIdx.x * PT_SORT_TILE;
+    for (int e = threadIdx.x; e < PT_SORT_TILE; e += 256) {
+        const int i = tile0 + e;
+        if (i < n) atomicAdd(&cnt[(keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = cnt[threadIdx.x];
+}
+// exclusive scan of hist (digit-major) in place, one block: each thread scans a contiguous slice, then the slice totals
+__global__ void __launch_bounds__(1024) k_sort_scan(int m, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t part[1024];
+    const int per = (m + 1023) / 1024, lo = threadIdx.x * per, hi = min(lo + per, m);
+    uint32_t run = 0u;
+    for (int i = lo; i < hi; ++i) run += hist[i];
+    part[threadIdx.x] = run;
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t acc = 0u; for (int t = 0; t < 1024; ++t) { const uint32_t c = part[t]; part[t] = acc; acc += c; } }
+    __syncthreads();
+    run = part[threadIdx.x];
+    for (int i = lo; i < hi; ++i) { const uint32_t c = hist[i]; hist[i] = run; run += c; }
+}
+__global__ void __launch_bounds__(256) k_sort_scatter(int n, int shift, const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                                                      const uint32_t* __restrict__ hist, uint32_t* __restrict__ keys_out,
+                                                      uint32_t* __restrict__ vals_out) {
+    __shared__ uint32_t warp_hist[8][256], cnt[256], base[256];
+    base[threadIdx.x] = hist[(size_t)threadIdx.x * gridDim.x + blockIdx.x];   // first output slot of this tile's keys with digit d
+    const int tile0 = blockIdx.x * PT_SORT_TILE;
+    for (int round = 0; round < PT_SORT_ITEMS; ++round) {
+        const int i = tile0 + round * 256 + (int)threadIdx.x;
+        const bool valid = i < n;
+        const uint32_t key = valid ? keys_in[i] : 0u, val = valid ? vals_in[i] : 0u, digit = (key >> shift) & 255u;
+        const uint32_t r = block_digit_rank(digit, valid, warp_hist, cnt);     // (its first barrier also orders the write of base[])
+        if (valid) { const uint32_t pos = base[digit] + r; keys_out[pos] = key; vals_out[pos] = val; }
+        __syncthreads();
+        base[threadIdx.x] += cnt[threadIdx.x];
+        __syncthreads();
+    }
 }
 
 __device__ __forceinline__ int lbvh_delta(const uint32_t* __restrict__ codes, int n, int i, int j) {

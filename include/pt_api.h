@@ -92,7 +92,7 @@ enum {
                                    tree is hit, like SceneBVH::TraceRay does (bvh.cu:175-180); removes most of the
                                    long-range graze-class differences at the price of more primitive tests. default 0 */
     PT_OPT_COUNT_STEPS = 8,     /* 1: use the instrumented traversal kernel that counts node visits / primitive tests */
-    PT_OPT_TRAV_INNER_RUN = 7,  /* tuning: inner-node steps a lane may take before the warp regroups for leaf tests */
+    PT_OPT_TRAV_INNER_RUN = 7,  /* tuning: inner-node steps a lane may take before the warp regroups for leaf tests (default 6) */
     PT_OPT_SAH_PASSES = 10,     /* SAH refit passes (tree rotations) after the LBVH build; default 4, 0 = plain LBVH */
     PT_OPT_ENTRY_GRID = 12,     /* finest level of the ENTRY GRID (default 0: off, every walk starts at the root; 12 = as fine as the
                                    scene allows).  Level l
@@ -201,6 +201,9 @@ int pt_raygen_batch(pt_scene* s, const pt_camera* cam, int n, const int32_t* xy,
 int pt_sky_lookup(pt_scene* s, int n, const float* dir3, float* rgb3);
 /* the uniforms the render path draws for (pixel, sample, slot): u4 = n x 4 */
 int pt_philox_uniforms(pt_scene* s, int n, uint64_t seed, const uint32_t* pixel_sample_slot3, float* u4);
+/* the LBVH build's own radix sort (pt_lbvh.cuh; round 1 used cub) on caller-supplied 32-bit codes: stable, ascending;
+ * slots_sorted[i] = input position of codes_sorted[i].  The scene needs pt_build again afterwards. */
+int pt_sort_code_pairs(pt_scene* s, int n, const uint32_t* codes, uint32_t* codes_sorted, uint32_t* slots_sorted);
 /* MotionalCamera::GetCopy basis (host math): out19 = u v w top_left horizontal vertical dist_to_focus */
 int pt_camera_basis(const pt_camera* cam, float out19[19]);
 

@@ -135,7 +135,8 @@ def test_update_prim_matches_the_references_own_update_object(ref_oracle, sky):
 
 
 def test_rebuild_after_update_is_cheap_at_100k_primitives(sky):
-    """pt_build after one pt_update_prim at C3's size: no host-side sort any more (it took 35 ms in round 1)."""
+    """pt_build after one pt_update_prim at C3's size: no host-side sort any more (it took 35 ms in round 1), only the moved
+    primitives are restaged and the two geometry arrays re-uploaded from page-locked memory: 1.0 ms measured (0.85 ms of it the device LBVH)."""
     import time
     sc = scenes.stress_field(100000, 320, 180)
     r = api.Renderer(sc, sky)
@@ -144,5 +145,21 @@ def test_rebuild_after_update_is_cheap_at_100k_primitives(sky):
         r.update_prim(7, sc.center[7] + np.float32([0.0, 0.0, 0.25 * k]), float(sc.radius[7]), 0.0, float(sc.height[7]))
         t0 = time.perf_counter(); r.build(); walls.append((time.perf_counter() - t0) * 1e3)
     r.render(sc.camera, 1, 8, seed=1)
-    assert min(walls) < 6.0, f"pt_build after an update: {walls} ms"
+    assert min(walls) < 3.0, f"pt_build after an update: {walls} ms"
+    r.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 256, 2047, 2048, 2049, 8192, 8193, 200001])
+def test_lbvh_radix_sort_is_a_stable_sort(n):
+    """The build's hand-written radix sort (one-block path up to 2048 keys, histogram / scan / scatter passes above) against
+    numpy's stable argsort: 30-bit codes like the Morton keys, plus heavy duplication (coincident primitives share a code and
+    the Karras tie-break relies on their input order) and full 32-bit keys."""
+    r = api.Renderer()
+    rng = np.random.RandomState(n)
+    for codes in (rng.randint(0, 1 << 30, n).astype(np.uint32), rng.randint(0, 7, n).astype(np.uint32),
+                  rng.randint(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32), np.zeros(n, np.uint32),
+                  np.arange(n, 0, -1).astype(np.uint32)):
+        ks, vs = r.sort_code_pairs(codes)
+        order = np.argsort(codes, kind="stable")
+        assert np.array_equal(vs, order.astype(np.uint32)) and np.array_equal(ks, codes[order])
     r.close()
