@@ -45,7 +45,7 @@ class PtStats(C.Structure):
 EXPORTS = [
     "pt_scene_create", "pt_scene_destroy", "pt_set_option", "pt_set_stream", "pt_add_sphere", "pt_add_platform",
     "pt_add_cylinder", "pt_set_material", "pt_update_prim", "pt_set_sky_rgba8", "pt_build", "pt_render_frame",
-    "pt_render_frame_async", "pt_synchronize", "pt_reset_accum", "pt_ensure_frame", "pt_read_accum", "pt_accum_device_ptr",
+    "pt_render_frame_async", "pt_synchronize", "pt_reset_accum", "pt_ensure_frame", "pt_read_accum", "pt_read_accum_begin", "pt_read_accum_end", "pt_accum_device_ptr",
     "pt_get_stats", "pt_dispatch_ray", "pt_dispatch_ray_frame", "pt_dispatch_ray_begin", "pt_dispatch_ray_end", "pt_texture_create_rgba8", "pt_texture_destroy", "pt_trace_rays", "pt_last_trace_steps",
     "pt_shade_batch", "pt_raygen_batch", "pt_sky_lookup", "pt_philox_uniforms", "pt_sort_code_pairs", "pt_camera_basis", "pt_camera_control",
     "pt_last_error",
@@ -82,6 +82,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.pt_render_frame_async.argtypes = lib.pt_render_frame.argtypes
     lib.pt_read_accum.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     lib.pt_ensure_frame.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.pt_read_accum_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.pt_read_accum_end.argtypes = [C.c_void_p]
     lib.pt_set_sky_rgba8.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     lib.pt_dispatch_ray.argtypes = [C.c_void_p, C.POINTER(PtCamera), C.c_int, C.c_uint64, C.c_uint32, C.c_void_p,
                                     C.c_size_t]
@@ -275,6 +277,13 @@ class Renderer:
             out = np.empty((h, w, 4), np.float32)
         self._check(self.lib.pt_read_accum(self.h, out.ctypes.data, out.size))
         return out
+
+    def read_accum_begin(self, out: np.ndarray):
+        """First half of a pipelined read-back into `out` (page-locked for a truly asynchronous copy); pair with read_accum_end."""
+        self._check(self.lib.pt_read_accum_begin(self.h, out.ctypes.data, out.size))
+
+    def read_accum_end(self):
+        self._check(self.lib.pt_read_accum_end(self.h))
 
     def accum_device_ptr(self):
         p = C.c_void_p(); n = C.c_size_t()

@@ -180,6 +180,10 @@ struct pt_scene {
     size_t stage_events_used = 0;
     bool frame_recorded = false;
     DevBuf<float4> read_tmp;
+    // pipelined read-back (pt_read_accum_begin / _end): two device staging buffers, the D2H copy on the copy stream
+    DevBuf<float4> read_pipe[2];
+    cudaEvent_t read_ready[2] = {nullptr, nullptr}, read_done[2] = {nullptr, nullptr};
+    uint64_t read_begun = 0, read_ended = 0;
 };
 
 namespace {
@@ -868,6 +872,13 @@ void release_display_host(pt_scene* s) {
         s->pipe_filtered[k] = s->pipe_copied[k] = nullptr;
     }
     s->pipe_bytes = 0; s->pipe_begun = s->pipe_ended = 0;
+    for (int k = 0; k < 2; ++k) {
+        s->read_pipe[k].release();
+        if (s->read_ready[k]) cudaEventDestroy(s->read_ready[k]);
+        if (s->read_done[k]) cudaEventDestroy(s->read_done[k]);
+        s->read_ready[k] = s->read_done[k] = nullptr;
+    }
+    s->read_begun = s->read_ended = 0;
     if (s->disp_host) cudaFreeHost(s->disp_host);
     s->disp_host = nullptr; s->disp_host_bytes = 0;
 }
@@ -1185,6 +1196,40 @@ int pt_read_accum(pt_scene* s, float* rgba, size_t nfloats) {
     s->stats.launches += 1;
     CK(cudaMemcpyAsync(rgba, s->read_tmp.p, npix * sizeof(float4), cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
+    return PT_OK;
+}
+
+// Read-back in two halves: _begin normalises the SUM buffer into a device staging buffer on the scene's stream and enqueues the
+// D2H copy on the copy stream; _end waits for the OLDEST copy begun.  With one read-back always in flight the copy of frame i
+// (33 MB at 1080p: 1.5 ms over PCIe) runs under the render of frame i + 1, and the scene's stream never waits for the host.
+int pt_read_accum_begin(pt_scene* s, float* rgba, size_t nfloats) {
+    PT_ON_SCENE_DEVICE(s);
+    if (!s || !rgba) return fail(PT_ERR_INVALID, "null argument");
+    const size_t npix = (size_t)s->width * s->height;
+    if (npix == 0 || nfloats != 4 * npix) return fail(PT_ERR_INVALID, "nfloats must be 4*width*height of the last frame");
+    if (s->read_begun - s->read_ended >= 2) return fail(PT_ERR_INVALID, "two read-backs are already in flight: call pt_read_accum_end first");
+    const int k = (int)(s->read_begun & 1);
+    if (!s->copy_stream) CK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+    if (!s->read_ready[k]) CK(cudaEventCreateWithFlags(&s->read_ready[k], cudaEventDisableTiming));
+    if (!s->read_done[k]) CK(cudaEventCreateWithFlags(&s->read_done[k], cudaEventDisableTiming));
+    CK(s->read_pipe[k].reserve(npix));
+    // staging buffer k was last read by the copy begun two calls ago, which _end has waited for (at most two in flight)
+    k_read_accum<<<(unsigned)((npix + 255) / 256), 256, 0, s->stream>>>((uint32_t)npix, s->accum.p, s->read_pipe[k].p);
+    s->stats.launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(s->read_ready[k], s->stream));
+    CK(cudaStreamWaitEvent(s->copy_stream, s->read_ready[k], 0));
+    CK(cudaMemcpyAsync(rgba, s->read_pipe[k].p, npix * sizeof(float4), cudaMemcpyDeviceToHost, s->copy_stream));
+    CK(cudaEventRecord(s->read_done[k], s->copy_stream));
+    ++s->read_begun;
+    return PT_OK;
+}
+int pt_read_accum_end(pt_scene* s) {
+    PT_ON_SCENE_DEVICE(s);
+    if (!s) return fail(PT_ERR_INVALID, "null scene");
+    if (s->read_begun == s->read_ended) return fail(PT_ERR_INVALID, "no read-back in flight");
+    CK(cudaEventSynchronize(s->read_done[s->read_ended & 1]));
+    ++s->read_ended;
     return PT_OK;
 }
 

@@ -153,6 +153,12 @@ int pt_reset_accum(pt_scene* s);
 /* mean radiance per pixel: rgba[4*(y*width+x)+{0,1,2}] = sum/samples, [3] = samples accumulated.
  * nfloats must be 4*width*height. */
 int pt_read_accum(pt_scene* s, float* rgba, size_t nfloats);
+/* pt_read_accum in two halves, for callers that render frame after frame (the video path, config C5): _begin enqueues the
+ * normalisation and the device-to-host copy (rgba should be page-locked for the copy to be asynchronous) and returns; _end waits
+ * for the oldest read-back begun.  At most two may be in flight; with begin(i+1) before end(i) the copy of frame i runs under the
+ * render of frame i+1.  rgba must stay valid until its _end. */
+int pt_read_accum_begin(pt_scene* s, float* rgba, size_t nfloats);
+int pt_read_accum_end(pt_scene* s);
 /* the device-resident SUM buffer (float4 per pixel: r,g,b,samples) for the caller's own reduction
  * across GPUs (torch.distributed / NCCL); valid until the frame size changes or the scene dies */
 int pt_accum_device_ptr(pt_scene* s, float** dptr, size_t* nfloats);

@@ -163,3 +163,28 @@ def test_lbvh_radix_sort_is_a_stable_sort(n):
         order = np.argsort(codes, kind="stable")
         assert np.array_equal(vs, order.astype(np.uint32)) and np.array_equal(ks, codes[order])
     r.close()
+
+
+def test_pipelined_read_back_delivers_the_same_frames(sky):
+    """pt_read_accum_begin / _end (copy of frame i on the copy stream under the render of frame i+1) == pt_read_accum, frame by frame."""
+    import torch
+    sc = scenes.sphere_field(300, 320, 180)
+    a, b = api.Renderer(sc, sky), api.Renderer(sc, sky)
+    want = []
+    for f in range(5):
+        a.reset_accum(); a.render(sc.camera, 3, 8, seed=f); want.append(a.read_accum().copy())
+    bufs = [torch.empty((180, 320, 4), dtype=torch.float32, pin_memory=True).numpy() for _ in range(2)]
+    got = []
+    for f in range(5):
+        b.reset_accum(); b.render(sc.camera, 3, 8, seed=f, sync=False)
+        b.read_accum_begin(bufs[f & 1])
+        if f >= 1:
+            b.read_accum_end(); got.append(bufs[(f - 1) & 1].copy())
+    with pytest.raises(api.PtError):                       # one in flight + two more = three: refused
+        b.read_accum_begin(bufs[1]); b.read_accum_begin(bufs[0])
+    b.read_accum_end(); got.append(bufs[0].copy())
+    b.read_accum_end()
+    with pytest.raises(api.PtError):
+        b.read_accum_end()                                 # nothing in flight
+    assert len(got) == 5 and all(np.array_equal(g, w) for g, w in zip(got, want))
+    a.close(); b.close()
