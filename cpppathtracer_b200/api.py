@@ -19,7 +19,7 @@ LIB_PATH_GRID = os.path.join(_HERE, "libpt_b200_grid.so")  # default arithmetic 
 
 PT_OPT_WAVE_PATHS, PT_OPT_STAGE_TIMING, PT_OPT_TIE_ORDER, PT_OPT_SKY_QUARTER_ROWS = 1, 2, 3, 4
 PT_OPT_TRAV_INNER_RUN, PT_OPT_COUNT_STEPS, PT_OPT_REF_LEAF_BOXES, PT_OPT_SAH_PASSES, PT_OPT_SAH_TREELETS = 7, 8, 9, 10, 11
-PT_OPT_ENTRY_GRID, PT_OPT_ENTRY_CELLS_PER_PRIM = 12, 13
+PT_OPT_ENTRY_GRID, PT_OPT_ENTRY_CELLS_PER_PRIM, PT_OPT_SPLIT_WALK = 12, 13, 14
 
 
 class PtMaterial(C.Structure):

@@ -121,6 +121,10 @@ struct pt_scene {
     int opt_entry_grid = 0;        // finest level the entry grid may use (0, the default: no grid, every walk starts at the root;
                                    // the grid halves the node visits per ray but not the warp's longest walk: DESIGN.md section 3.4)
     int opt_entry_cells_per_prim = 2;   // the finest level has at most this many blocks per primitive
+    int opt_split_walk = 0;             // entry-grid library: 1 = bounces run as k_shade_classify + k_walk (rays binned by level class)
+    DevBuf<float4> rq_p, rq_d, rq_thr;  // ... and the ray queue between the two (two two-ended regions, single-buffered)
+    DevBuf<BounceCtrl> rctrl;
+    uint32_t rq_capacity = 0;
     // device scene
     DevBuf<float4> geo0, geo1, nodes, leaf_mn, leaf_mx, leaf_c, inner_mn, inner_mx, test_mn, test_mx;
     DevBuf<MaterialRec> mats;
@@ -162,7 +166,7 @@ struct pt_scene {
     pt_stats stats{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> stage_events;
-    int grid_bounce = 0;
+    int grid_bounce = 0, grid_walk = 0;
     DevBuf<unsigned char> node_height;
     DevBuf<float> sah_dev;
     float sah_host[2] = {0.f, 0.f};   // SAH cost (sum of inner areas / root area) before and after the refit passes
@@ -667,6 +671,22 @@ int render_async(pt_scene* s, const pt_camera* cam, int spp, int max_depth, uint
     rc = ensure_queues(s, npix, spp_per_wave, max_depth); if (rc) return rc;
     const uint32_t cap = npix * spp_per_wave;
     cudaStream_t st = s->stream;
+#if PT_ENTRY_GRID_CODE
+    const bool split = s->opt_split_walk && s->grid.lmax >= 1;
+    if (split) {
+        if (s->rq_capacity < s->capacity) {
+            s->rq_p.release(); s->rq_d.release(); s->rq_thr.release();
+            CK(s->rq_p.reserve(2 * (size_t)s->capacity)); CK(s->rq_d.reserve(2 * (size_t)s->capacity)); CK(s->rq_thr.reserve(2 * (size_t)s->capacity));
+            s->rq_capacity = s->capacity;
+        }
+        CK(s->rctrl.reserve((size_t)max_depth + 2));
+        if (!s->grid_walk) {
+            int occ = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_walk<false>, 32 * PT_BOUNCE_WARPS, 0));
+            s->grid_walk = s->sm_count * std::max(occ, 1);
+        }
+    }
+#endif
     const CameraFrame frame = to_device_frame(cam);
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
     BounceArgs args;
@@ -690,6 +710,9 @@ int render_async(pt_scene* s, const pt_camera* cam, int spp, int max_depth, uint
         const uint32_t ns = std::min<uint32_t>(spp_per_wave, (uint32_t)spp - s0);
         const uint32_t n_paths = npix * ns;
         CK(cudaMemsetAsync(s->ctrl.p, 0, ((size_t)max_depth + 2) * sizeof(BounceCtrl), st));
+#if PT_ENTRY_GRID_CODE
+        if (split) CK(cudaMemsetAsync(s->rctrl.p, 0, ((size_t)max_depth + 2) * sizeof(BounceCtrl), st));
+#endif
         args.first_sample = first_sample + s0; args.n_paths = n_paths;
         // segment 0: camera rays -> hit queue 0
         CK(stage_event());
@@ -708,6 +731,22 @@ int render_async(pt_scene* s, const pt_camera* cam, int spp, int max_depth, uint
             args.segment = k; args.trace = k < max_depth ? 1 : 0;
             args.ctrl_in = ctrl + (k - 1); args.ctrl_out = ctrl + k;
             args.hq_in = hit_queues(s, (k - 1) & 1); args.hq_out = hit_queues(s, k & 1);
+#if PT_ENTRY_GRID_CODE
+            if (split && args.trace) {
+                // two launches: shade + classify by entry-grid level, then walk one level class per chunk
+                args.rctrl = s->rctrl.p + k;
+                args.rq.p = s->rq_p.p; args.rq.d = s->rq_d.p; args.rq.thr = s->rq_thr.p; args.rq.capacity = s->rq_capacity;
+                if (s->opt_count_steps) {
+                    k_shade_classify<true><<<s->grid_bounce, 32 * PT_BOUNCE_WARPS, 0, st>>>(args);
+                    k_walk<true><<<s->grid_walk, 32 * PT_BOUNCE_WARPS, 0, st>>>(args);
+                } else {
+                    k_shade_classify<false><<<s->grid_bounce, 32 * PT_BOUNCE_WARPS, 0, st>>>(args);
+                    k_walk<false><<<s->grid_walk, 32 * PT_BOUNCE_WARPS, 0, st>>>(args);
+                }
+                ++launches;
+                continue;
+            }
+#endif
             launch_bounce<SRC_HITS>(s, args, st);
         }
         CK(stage_event());
@@ -1031,6 +1070,7 @@ void pt_scene_destroy(pt_scene* s) {
     s->ctrl.release(); s->q_o.release(); s->q_d.release(); s->seg_counter.release();
     s->node_height.release(); s->sah_dev.release(); s->grid_cells.release(); s->grid_levels.release();
     s->st_g0.release(); s->st_g1.release(); s->st_orig.release(); s->st_tree.release(); s->nodes4.release();
+    s->rq_p.release(); s->rq_d.release(); s->rq_thr.release(); s->rctrl.release();
     for (int k = 0; k < 2; ++k) { s->hq_p[k].release(); s->hq_d[k].release(); s->hq_thr[k].release(); s->scratch_i[k].release(); }
     for (auto& b : s->scratch_f) b.release();
     s->disp_color.release(); s->disp_normal.release(); s->disp_mix.release(); s->disp_depth.release(); s->disp_bgra.release();
@@ -1067,6 +1107,11 @@ int pt_set_option(pt_scene* s, int option, int64_t value) {
         case PT_OPT_ENTRY_CELLS_PER_PRIM:
             if (value < 1 || value > 64) return fail(PT_ERR_INVALID, "PT_OPT_ENTRY_CELLS_PER_PRIM: 1 .. 64");
             s->opt_entry_cells_per_prim = (int)value; s->dirty = true; return PT_OK;
+        case PT_OPT_SPLIT_WALK:
+#if !PT_ENTRY_GRID_CODE
+            if (value != 0) return fail(PT_ERR_INVALID, "this build carries no entry-grid code in its kernels: use libpt_b200_grid.so");
+#endif
+            s->opt_split_walk = value != 0; return PT_OK;
         case PT_OPT_TRAV_INNER_RUN:
             if (value < 1 || value > 1024) return fail(PT_ERR_INVALID, "inner_run must be 1..1024");
             s->opt_inner_run = (int)value; return PT_OK;

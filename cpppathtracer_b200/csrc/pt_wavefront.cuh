@@ -255,6 +255,35 @@ __device__ __forceinline__ void lane_begin(const SceneDev& sc, LaneRay& r, int* 
     lane_platforms(sc, r.o, r.d, r.tmin, r.best_t, r.best_code);
     lane_setup(sc, r, stack);
 }
+#if PT_ENTRY_GRID_CODE
+// The entry-grid level of a ray without starting its walk (the split pipeline classifies rays by it): the level lane_setup
+// would pick -- 0 for a long segment that starts at the root --, or -1 when the ray misses the box of everything in the tree.
+__device__ __forceinline__ int ray_level(const SceneDev& sc, float3 o, float3 d, float tmin, float best_t) {
+    const EntryGrid& g = sc.grid;
+    if (sc.n_tree_prims <= 0) return -1;
+    if (g.lmax < 0) return 0;
+    const float ix = cull_rcp(fabsf(d.x) > 1e-18f ? d.x : copysignf(1e-18f, d.x));
+    const float iy = cull_rcp(fabsf(d.y) > 1e-18f ? d.y : copysignf(1e-18f, d.y));
+    const float iz = cull_rcp(fabsf(d.z) > 1e-18f ? d.z : copysignf(1e-18f, d.z));
+    const float ox = o.x * ix, oy = o.y * iy, oz = o.z * iz;
+    const float slack = 4.0f * 1.1920929e-7f * fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fabsf(oz));
+    const float x0 = fmaf(g.org.x, ix, -ox), x1 = fmaf(g.hi.x, ix, -ox);
+    const float y0 = fmaf(g.org.y, iy, -oy), y1 = fmaf(g.hi.y, iy, -oy);
+    const float z0 = fmaf(g.org.z, iz, -oz), z1 = fmaf(g.hi.z, iz, -oz);
+    const float t0 = fmaxf(fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fminf(z0, z1)) - slack, tmin - slack);
+    const float t1 = fminf(fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1)) + slack, best_t * 1.0000005f + slack);
+    if (!(t0 <= t1)) return -1;
+    const float ax = fmaf(t0, d.x, o.x), ay = fmaf(t0, d.y, o.y), az = fmaf(t0, d.z, o.z);
+    const float bx = fmaf(t1, d.x, o.x), by = fmaf(t1, d.y, o.y), bz = fmaf(t1, d.z, o.z);
+    const float ex = fmaxf(fminf(fmaxf(ax, bx), g.hi.x) - fmaxf(fminf(ax, bx), g.org.x), 0.f);
+    const float ey = fmaxf(fminf(fmaxf(ay, by), g.hi.y) - fmaxf(fminf(ay, by), g.org.y), 0.f);
+    const float ez = fmaxf(fminf(fmaxf(az, bz), g.hi.z) - fmaxf(fminf(az, bz), g.org.z), 0.f);
+    const float ext = fmaxf(fmaxf(ex, ey), ez) * 1.000001f + 1e-30f;
+    int l = g.k + 126 - (__float_as_int(ext) >> 23);
+    l = l > g.lmax ? g.lmax : l;
+    return l < 0 ? 0 : l;
+}
+#endif
 
 // One 64-byte node = two 256-bit loads (LDG.E.256, new on sm_100): half the LSU instructions and L1 wavefronts
 // of four 128-bit loads -- the walk is bound by the L1 wavefront pipe on incoherent bounces.
@@ -410,6 +439,10 @@ struct BounceArgs {
     const float2* ray_range;
     uint2* slot_hit;
     uint32_t n_rays;
+    // split pipeline (PT_OPT_SPLIT_WALK, entry-grid library only): k_shade_classify files the rays of this segment, by
+    // entry-grid level class, into rq (control block rctrl); k_walk reads them from there
+    HitQueues rq;             // same layout as the hit queues: p = (origin, pixel), d = (dir, sample), thr = (throughput, -)
+    BounceCtrl* rctrl;
     unsigned long long* step_counters;   // COUNT_STEPS: [0] inner nodes visited, [1] primitive tests
     uint32_t* ray_steps;                 // COUNT_STEPS + SRC_RAYS: visits per ray (diagnostics)
 };
@@ -623,6 +656,136 @@ __global__ void PT_BOUNCE_BOUNDS k_bounce(const BounceArgs a) {
         if (lane == 0) { atomicAdd(&a.step_counters[0], (unsigned long long)n_inner); atomicAdd(&a.step_counters[1], (unsigned long long)n_leaf); }
     }
 }
+
+#if PT_ENTRY_GRID_CODE
+// ---- the split pipeline (PT_OPT_SPLIT_WALK) ---------------------------------------------------
+// A warp walks until its LONGEST ray is done, and with the entry grid the level of a ray predicts the length of its walk.
+// So a bounce becomes two launches: k_shade_classify shades the hits of segment k-1 (one shader per chunk, as k_bounce
+// does) and files each surviving ray into one of four LEVEL CLASSES (two two-ended regions, like the hit queues; a ray
+// that misses the box of the tree and every platform ends at the sky right there); k_walk takes 32-ray chunks of ONE
+// class, longest class first, walks them and files the hits by shader.  The price is one 48-byte ray record through HBM
+// per ray and a second launch per segment; the camera launch stays fused (its rays are coherent already).
+__device__ __forceinline__ int level_class(const SceneDev& sc, int level) {
+    // class 1: levels <= lmax - 3 (long rays, and the root), 2: lmax - 2, 3: lmax - 1, 4: lmax (the shortest)
+    const int c = level - (sc.grid.lmax - 3);
+    return 1 + (c < 0 ? 0 : (c > 3 ? 3 : c));
+}
+template <bool COUNT_STEPS>
+__global__ void __launch_bounds__(32 * PT_BOUNCE_WARPS) k_shade_classify(const BounceArgs a) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const SceneDev& sc = a.sc;
+    uint32_t chunk_end[NUM_BINS], bin_n[NUM_BINS];
+    uint32_t total = 0;
+#pragma unroll
+    for (int b = 0; b < NUM_BINS; ++b) { bin_n[b] = a.ctrl_in->bin_count[b].v; total += (bin_n[b] + 31u) >> 5; chunk_end[b] = total; }
+    const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
+    uint32_t grab = total / (n_warps * 8u);
+    grab = grab < 1u ? 1u : (grab > 4u ? 4u : grab);
+    const bool last_shade = a.segment >= a.max_depth;
+    while (true) {
+        uint32_t first = 0;
+        if (lane == 0) first = atomicAdd(&a.ctrl_in->shade_head.v, grab);
+        first = __shfl_sync(PT_FULL, first, 0);
+        if (first >= total) break;
+        const uint32_t end = first + grab < total ? first + grab : total;
+        for (uint32_t chunk = first; chunk < end; ++chunk) {
+            int bin = 0;
+            uint32_t first_chunk = 0u, n_bin = bin_n[0];
+#pragma unroll
+            for (int b = 1; b < NUM_BINS; ++b)
+                if (chunk >= chunk_end[b - 1]) { bin = b; first_chunk = chunk_end[b - 1]; n_bin = bin_n[b]; }
+            const uint32_t item = ((chunk - first_chunk) << 5) + lane;
+            bool alive = false;
+            float3 o = f3(0.f, 0.f, 0.f), d = f3(0.f, 0.f, 0.f), thr = f3(1.f, 1.f, 1.f);
+            uint32_t pixel = 0, s = 0;
+            if (item < n_bin) alive = shade_hit_item(a, bin, item, last_shade, o, d, thr, pixel, s);
+            int cls = -1;
+            if (alive) {
+                float best_t = PT_TMAX; uint32_t best_code;
+                lane_platforms(sc, o, d, PT_BOUNCE_TMIN, best_t, best_code);
+                const int level = ray_level(sc, o, d, PT_BOUNCE_TMIN, best_t);
+                if (level < 0 && best_code == PT_MISS_CODE) shade_miss(a, d, thr, (size_t)s * a.npix + pixel, false);   // nothing in its way
+                else cls = level < 0 ? NUM_BINS - 1 : level_class(sc, level);      // (a platform hit without a walk: shortest class)
+            }
+            uint32_t my_mask = 0u, lane_mask = 0u;
+#pragma unroll
+            for (int b = 1; b < NUM_BINS; ++b) {
+                const uint32_t m = __ballot_sync(PT_FULL, cls == b);
+                if (cls == b) my_mask = m;
+                if ((int)lane == b) lane_mask = m;
+            }
+            uint32_t base = 0u;
+            if (lane_mask) base = atomicAdd(&a.rctrl->bin_count[lane & 7u].v, (uint32_t)__popc(lane_mask));
+            base = __shfl_sync(PT_FULL, base, cls & 7);
+            if (cls >= 1) {
+                const size_t j = hit_slot(a.rq.capacity, cls, base + (uint32_t)__popc(my_mask & ((1u << lane) - 1u)));
+                __stcs(&a.rq.p[j], make_float4(o.x, o.y, o.z, __uint_as_float(pixel)));
+                __stcs(&a.rq.d[j], make_float4(d.x, d.y, d.z, __uint_as_float(s)));
+                __stcs(&a.rq.thr[j], make_float4(thr.x, thr.y, thr.z, 0.f));
+            }
+        }
+    }
+}
+template <bool COUNT_STEPS>
+__global__ void __launch_bounds__(32 * PT_BOUNCE_WARPS) k_walk(const BounceArgs a) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const SceneDev& sc = a.sc;
+    uint32_t chunk_end[NUM_BINS], bin_n[NUM_BINS];
+    uint32_t total = 0;
+#pragma unroll
+    for (int b = 0; b < NUM_BINS; ++b) { bin_n[b] = a.rctrl->bin_count[b].v; total += (bin_n[b] + 31u) >> 5; chunk_end[b] = total; }
+    const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
+    uint32_t grab = total / (n_warps * 8u);
+    grab = grab < 1u ? 1u : (grab > 4u ? 4u : grab);
+    uint32_t traced = 0, n_inner = 0, n_leaf = 0;
+    int stack[PT_STACK];
+    while (true) {
+        uint32_t first = 0;
+        if (lane == 0) first = atomicAdd(&a.rctrl->shade_head.v, grab);
+        first = __shfl_sync(PT_FULL, first, 0);
+        if (first >= total) break;
+        const uint32_t end = first + grab < total ? first + grab : total;
+        for (uint32_t chunk = first; chunk < end; ++chunk) {
+            int bin = 0;
+            uint32_t first_chunk = 0u, n_bin = bin_n[0];
+#pragma unroll
+            for (int b = 1; b < NUM_BINS; ++b)
+                if (chunk >= chunk_end[b - 1]) { bin = b; first_chunk = chunk_end[b - 1]; n_bin = bin_n[b]; }
+            const uint32_t item = ((chunk - first_chunk) << 5) + lane;
+            const bool alive = item < n_bin;
+            LaneRay r;
+            r.tmin = PT_BOUNCE_TMIN; r.best_t = PT_TMAX; r.best_code = PT_MISS_CODE; r.node = PT_SENTINEL; r.sp = 0;
+            r.o = r.d = f3(0.f, 0.f, 0.f); r.ix = r.iy = r.iz = r.ox = r.oy = r.oz = r.slack = r.lo = r.hi = 0.f;
+            float3 thr = f3(1.f, 1.f, 1.f);
+            uint32_t pixel = 0, s = 0;
+            if (alive) {
+                const size_t q = hit_slot(a.rq.capacity, bin, item);
+                const float4 p4 = __ldcs(&a.rq.p[q]), d4 = __ldcs(&a.rq.d[q]), t4 = __ldcs(&a.rq.thr[q]);
+                r.o = f3(p4.x, p4.y, p4.z); r.d = f3(d4.x, d4.y, d4.z); thr = f3(t4.x, t4.y, t4.z);
+                pixel = __float_as_uint(p4.w); s = __float_as_uint(d4.w);
+                lane_begin(sc, r, stack); ++traced;
+            }
+            while (__any_sync(PT_FULL, alive && r.node != PT_SENTINEL)) {
+                if (alive) {
+                    int k = 0;
+#pragma unroll 1
+                    while (r.node >= 0 && r.node != PT_SENTINEL && k < a.inner_run) { lane_inner(sc, r, stack); ++k; if (COUNT_STEPS) ++n_inner; }
+                }
+                if (alive && r.node < 0) { lane_leaf(sc, r, stack); if (COUNT_STEPS) ++n_leaf; }
+            }
+            file_hit(a, lane, alive, r.o, r.d, thr, pixel, s, r.best_t, r.best_code);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) traced += __shfl_xor_sync(PT_FULL, traced, o);
+    if (lane == 0 && traced) atomicAdd(&a.ctrl_out->rays.v, traced);
+    if (COUNT_STEPS) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { n_inner += __shfl_xor_sync(PT_FULL, n_inner, o); n_leaf += __shfl_xor_sync(PT_FULL, n_leaf, o); }
+        if (lane == 0) { atomicAdd(&a.step_counters[0], (unsigned long long)n_inner); atomicAdd(&a.step_counters[1], (unsigned long long)n_leaf); }
+    }
+}
+#endif
 
 // ---- stage 3: accumulate the wave into the frame's SUM buffer, sample order, fp32 -------------------------
 // (the reference's Mix keeps a running mean of CLAMPED, denoised samples, path_tracer.cu:241-254; the

@@ -102,6 +102,8 @@ enum {
                                    node visits per segment 18.7 -> 7.7 on C3 and 9.7 -> 4.9 on C2, throughput +-1 % -- a warp walks until
                                    its LONGEST ray is done and long rays start at the root either way -- hence off by default. */
     PT_OPT_ENTRY_CELLS_PER_PRIM = 13, /* the finest level has at most this many blocks per primitive (default 2) */
+    PT_OPT_SPLIT_WALK = 14,     /* libpt_b200_grid.so only, with the entry grid on: 1 = every bounce runs as two launches, shade + classify
+                                   the rays by entry-grid level, then walk one level class per warp; images are identical */
     PT_OPT_SAH_TREELETS = 11    /* 1: the refit passes restructure 7-leaf treelets by dynamic programming instead of
                                    single rotations: lower SAH (C2 11.06 vs 11.24), but 1.5 ms instead of 0.06 ms per
                                    pass at 1 k primitives -- for scenes that are built once; default 0 */
