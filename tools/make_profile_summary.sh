@@ -1,5 +1,5 @@
 #!/bin/bash
-# Turns the files a profiling gpurun call left in gpurun_out/ into profiles/r01_<tag>_summary.md (+ the raw launch list,
+# (round 1 helper; round 2 assembled profiles/r02_*.md from tools/ncu_summary.py directly) Turns the files a profiling gpurun call left in gpurun_out/ into profiles/r01_<tag>_summary.md (+ the raw launch list,
 # the bench line and profiles/traverse_traffic.json).   usage: tools/make_profile_summary.sh v12 "title text"
 set -e
 tag="$1"; title="$2"
