@@ -510,7 +510,7 @@ __device__ __forceinline__ void file_hit(const BounceArgs& a, uint32_t lane, boo
     if (alive)
         obin = (best_code == PT_MISS_CODE) ? BIN_MISS : (int)(__float_as_uint(__ldg(&sc.geo1[best_code >> 3]).w) >> 28);
     // rays that leave the scene end here: the sky is looked up by the lanes that missed instead of sending a
-    // 56-byte record through a miss bin to the next launch (v7 did: +9 % on C2 without it)
+    // 48-byte record through a miss bin to the next launch (v7 did: +9 % on C2 without it)
     if (obin == BIN_MISS) { shade_miss(a, d, thr, (size_t)s * a.npix + pixel, a.segment == 0); obin = -1; }
     // a hit of the last allowed segment can only add emission: in a scene without emitters its path ends black, and
     // the shade-only launch that would find that out is not enqueued (render_async)

@@ -73,7 +73,7 @@ typedef struct pt_stats {
     uint32_t waves;           /* waves of the last pt_render_frame                            */
     uint64_t node_steps;      /* inner BVH nodes visited (only with PT_OPT_COUNT_STEPS)       */
     uint64_t prim_tests;      /* sphere / cylinder tests run (only with PT_OPT_COUNT_STEPS)   */
-    uint64_t hit_records;     /* 56-byte hit records that went through the hit queues (segments that hit) */
+    uint64_t hit_records;     /* 48-byte hit records that went through the hit queues (segments that hit) */
     float    bvh_sah_lbvh;    /* SAH cost (sum of inner-node areas / root area) of the Karras tree ...        */
     float    bvh_sah;         /* ... and after the SAH refit passes (PT_OPT_SAH_PASSES)                        */
     uint32_t entry_levels;    /* finest level of the entry grid built by the last pt_build (0: none)          */
