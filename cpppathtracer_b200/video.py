@@ -52,9 +52,24 @@ def render_video(scene, sky, n_frames: int = 120, spp: int = 64, max_depth: int 
     """Render this rank's frames.  Returns per-frame stats: frame, build_ms, render_ms, mpaths_s, wall_ms."""
     r = renderer or api.Renderer(scene, sky)
     cams = camera_path(scene.camera, n_frames)
-    host = np.empty((scene.camera.height, scene.camera.width, 4), np.float32)
+    shape = (scene.camera.height, scene.camera.width, 4)
+    try:                                    # page-locked frames make the read-back a true DMA; plain numpy works too
+        import torch
+        hosts = [torch.empty(shape, dtype=torch.float32, pin_memory=True).numpy() for _ in range(2)]
+    except Exception:
+        hosts = [np.empty(shape, np.float32) for _ in range(2)]
     stats = []
-    for f in frames_of_rank(n_frames, world, rank):
+    pending = None                          # (frame, buffer index) whose read-back is in flight
+
+    def deliver():
+        # the frame handed out here was copied to the host while the NEXT frame was being built and rendered
+        # (pt_read_accum_begin / _end, like the reference's render thread hands a finished frame to its callback)
+        f_done, k_done = pending
+        r.read_accum_end()
+        os.makedirs(out_dir, exist_ok=True)
+        write_ppm(os.path.join(out_dir, f"frame_{f_done:04d}.ppm"), hosts[k_done][..., :3])
+
+    for n, f in enumerate(frames_of_rank(n_frames, world, rank)):
         t0 = time.perf_counter()
         ids, centres = moving_spheres(scene, f)
         for p, c in zip(ids, centres):
@@ -64,9 +79,12 @@ def render_video(scene, sky, n_frames: int = 120, spp: int = 64, max_depth: int 
         r.render(cams[f], spp, max_depth, seed=seed)
         st = r.stats()
         if out_dir:
-            r.read_accum(host)
-            os.makedirs(out_dir, exist_ok=True)
-            write_ppm(os.path.join(out_dir, f"frame_{f:04d}.ppm"), host[..., :3])
+            r.read_accum_begin(hosts[n & 1])
+            if pending is not None:
+                deliver()
+            pending = (f, n & 1)
         stats.append({"frame": f, "build_ms": st["build_ms"], "render_ms": st["render_ms"],
                       "mpaths_s": st["paths"] / st["render_ms"] / 1e3, "wall_ms": (time.perf_counter() - t0) * 1e3})
+    if pending is not None:
+        deliver()
     return stats
