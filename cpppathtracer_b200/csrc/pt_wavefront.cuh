@@ -205,9 +205,7 @@ __device__ __forceinline__ void lane_setup(const SceneDev& sc, LaneRay& r, int* 
     r.top = PT_SENTINEL;
 #endif
     r.node = sc.n_tree_prims > 0 ? 0 : PT_SENTINEL;
-#if !PT_ENTRY_GRID_CODE
-    return;
-#endif
+#if PT_ENTRY_GRID_CODE
     const EntryGrid& g = sc.grid;
     if (g.lmax < 0 || sc.n_tree_prims <= 0) return;
     // ---- the ray as a segment: clipped to the gridded box and to [lo, hi] (tmin .. platform hit), same FMA slabs and
@@ -250,6 +248,7 @@ __device__ __forceinline__ void lane_setup(const SceneDev& sc, LaneRay& r, int* 
             if (f.w != PT_SENTINEL) stack_push(r, stack, f.w);
         }
     }
+#endif
 }
 __device__ __forceinline__ void lane_begin(const SceneDev& sc, LaneRay& r, int* stack) {
     lane_platforms(sc, r.o, r.d, r.tmin, r.best_t, r.best_code);

@@ -28,8 +28,18 @@ int main(void) {
     if (pt_read_accum(s, img, (size_t)4 * 64 * 36) != PT_OK) { printf("ERR %s\n", pt_last_error()); return 1; }
     double sum = 0.0;
     for (int i = 0; i < 64 * 36; ++i) sum += img[4 * i] + img[4 * i + 1] + img[4 * i + 2];
-    printf("OK samples %.0f mean %.4f version %s\n", img[3], sum / (3.0 * 64 * 36), pt_version());
-    free(img);
+    /* an object moves (SceneBVH::UpdateObject), the frame is rendered again and read back in two halves: the copy of a
+     * frame may run under the next frame's build and render (pt_read_accum_begin / _end) */
+    float c2[3] = {0.5f, 1.f, -0.5f};
+    float* img2 = (float*)malloc(sizeof(float) * 4 * 64 * 36);
+    if (pt_update_prim(s, id, c2, 1.0f, 0.f, 0.f) != PT_OK || pt_build(s) != PT_OK || pt_reset_accum(s) != PT_OK ||
+        pt_render_frame_async(s, &cam, 4, 8, 1u, 0u) != PT_OK || pt_read_accum_begin(s, img2, (size_t)4 * 64 * 36) != PT_OK ||
+        pt_read_accum_end(s) != PT_OK) { printf("ERR %s\n", pt_last_error()); return 1; }
+    int moved = memcmp(img, img2, sizeof(float) * 4 * 64 * 36) != 0;
+    pt_stats st;
+    pt_get_stats(s, &st);
+    printf("OK samples %.0f mean %.4f version %s moved %d build_ms %.3f\n", img[3], sum / (3.0 * 64 * 36), pt_version(), moved, st.build_ms);
+    free(img); free(img2);
     pt_scene_destroy(s);
     return 0;
 }

@@ -86,4 +86,4 @@ def test_abi_c_example_runs(tmp_path):
     exe = tmp_path / "abi_c_example"
     _compile_c("abi_c_example.c", exe)
     r = subprocess.run([str(exe)], capture_output=True, text=True)
-    assert r.returncode == 0 and r.stdout.startswith("OK samples 4 mean 0."), r.stdout + r.stderr
+    assert r.returncode == 0 and r.stdout.startswith("OK samples 4 mean 0.") and " moved 1 " in r.stdout, r.stdout + r.stderr
