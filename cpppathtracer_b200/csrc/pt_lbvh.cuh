@@ -287,6 +287,9 @@ __global__ void k_lbvh_hierarchy(int n, const uint32_t* __restrict__ codes, int2
 // distance to a full-sweep SAH build (C2: SAH cost 11.6 -> see DESIGN.md section 3.3) in one or two extra passes of
 // this kernel.  `height` (levels below a node) keeps the walk's stack bound: a rotation that would raise a subtree
 // above PT_LBVH_MAX_ROT_HEIGHT levels is refused unless the subtree was already that high.
+#ifndef PT_PACKED_SLABS
+#define PT_PACKED_SLABS 0     // 1: node layout and slab tests for packed FP32x2 arithmetic (FFMA2, new on sm_100)
+#endif
 #define PT_LBVH_MAX_ROT_HEIGHT 48
 __device__ __forceinline__ float box_area(float4 mn, float4 mx) {
     const float dx = mx.x - mn.x, dy = mx.y - mn.y, dz = mx.z - mn.z;
@@ -558,9 +561,16 @@ __global__ void k_lbvh_pack(int n, const uint32_t* __restrict__ sorted_ids, cons
     float3 ca, ha, cb, hb;
     centre_half(amn, amx, ca, ha);
     centre_half(bmn, bmx, cb, hb);
+#if PT_PACKED_SLABS
+    // (cx, cy) and (hx, hy) of a child sit in aligned pairs: the x and y slabs are evaluated by packed FFMA2 (pt_wavefront.cuh)
+    nodes[4 * i + 0] = make_float4(ca.x, ca.y, ha.x, ha.y);
+    nodes[4 * i + 1] = make_float4(cb.x, cb.y, hb.x, hb.y);
+    nodes[4 * i + 2] = make_float4(ca.z, ha.z, cb.z, hb.z);
+#else
     nodes[4 * i + 0] = make_float4(ca.x, ca.y, ca.z, ha.x);
     nodes[4 * i + 1] = make_float4(ha.y, ha.z, cb.x, cb.y);
     nodes[4 * i + 2] = make_float4(cb.z, hb.x, hb.y, hb.z);
+#endif
     nodes[4 * i + 3] = make_float4(__int_as_float(c0), __int_as_float(c1), 0.f, 0.f);
 }
 
@@ -677,9 +687,15 @@ __global__ void k_lbvh_single(const int* __restrict__ bvh_prims, const float4* _
     int c0 = ~((p << 2) | (__float_as_int(geo1[p].z) & 3));
     float3 c, h;
     centre_half(make_float4(b.mn.x, b.mn.y, b.mn.z, 0.f), make_float4(b.mx.x, b.mx.y, b.mx.z, 0.f), c, h);
+#if PT_PACKED_SLABS
+    nodes[0] = make_float4(c.x, c.y, h.x, h.y);
+    nodes[1] = make_float4(0.f, 0.f, -1.f, -1.f);           // negative half-extent: near > far, never entered
+    nodes[2] = make_float4(c.z, h.z, 0.f, -1.f);
+#else
     nodes[0] = make_float4(c.x, c.y, c.z, h.x);
     nodes[1] = make_float4(h.y, h.z, 0.f, 0.f);
     nodes[2] = make_float4(0.f, -1.f, -1.f, -1.f);          // negative half-extent: near > far, never entered
+#endif
     nodes[3] = make_float4(__int_as_float(c0), __int_as_float(c0), 0.f, 0.f);
 }
 

@@ -297,7 +297,50 @@ __device__ __forceinline__ void load_node(const float4* __restrict__ nodes, int 
                  : "l"(p + 2));
 }
 
+#if PT_PACKED_SLABS
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float a, float b) { f32x2 v; asm("mov.b64 %0, {%1,%2};" : "=l"(v) : "f"(a), "f"(b)); return v; }
+__device__ __forceinline__ void unpack2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+#endif
 __device__ __forceinline__ void lane_inner(const SceneDev& sc, LaneRay& r, int* stack) {
+#if PT_PACKED_SLABS
+    {
+        // node = (cax cay hax hay | cbx cby hbx hby) (caz haz cbz hbz | link a, link b, -, -): the x and y slabs of a child are one
+        // FFMA2 each for the centre distance, the near and the far plane (3 instead of 6 instructions), z stays scalar
+        const float4* p = sc.nodes + 4 * (size_t)r.node;
+        f32x2 ca, ha, cb, hb;
+        float caz, haz, cbz, hbz, la, lb, pad0, pad1;
+        asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(ca), "=l"(ha), "=l"(cb), "=l"(hb) : "l"(p));
+        asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(caz), "=f"(haz), "=f"(cbz), "=f"(hbz), "=f"(la), "=f"(lb), "=f"(pad0), "=f"(pad1) : "l"(p + 2));
+        const f32x2 ixy = pack2(r.ix, r.iy), noxy = pack2(-r.ox, -r.oy), axy = pack2(fabsf(r.ix), fabsf(r.iy)), naxy = pack2(-fabsf(r.ix), -fabsf(r.iy));
+        const float az = fabsf(r.iz);
+        const f32x2 ta = fma2(ca, ixy, noxy), tb = fma2(cb, ixy, noxy);
+        float nax, nay, fax, fay, nbx, nby, fbx, fby;
+        unpack2(fma2(ha, naxy, ta), nax, nay); unpack2(fma2(ha, axy, ta), fax, fay);
+        unpack2(fma2(hb, naxy, tb), nbx, nby); unpack2(fma2(hb, axy, tb), fbx, fby);
+        const float taz = fmaf(caz, r.iz, -r.oz), tbz = fmaf(cbz, r.iz, -r.oz);
+        const float lo = r.lo, hi = r.hi;
+        const float ea = fmaxf(fmaxf(nax, nay), fmaxf(fmaf(-haz, az, taz), lo));
+        const float xa = fminf(fminf(fax, fay), fminf(fmaf(haz, az, taz), hi));
+        const float eb = fmaxf(fmaxf(nbx, nby), fmaxf(fmaf(-hbz, az, tbz), lo));
+        const float xb = fminf(fminf(fbx, fby), fminf(fmaf(hbz, az, tbz), hi));
+        const bool ha_ = ea <= xa, hb_ = eb <= xb;
+        const int ca_ = __float_as_int(la), cb_ = __float_as_int(lb);
+        if (ha_ && hb_) {
+            const bool a_near = ea <= eb;
+            r.node = a_near ? ca_ : cb_;
+            const int far = a_near ? cb_ : ca_;
+            stack_push(r, stack, far);
+#if PT_PREFETCH_FAR
+            if (far >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(sc.nodes + 4 * (size_t)far));
+#endif
+        } else if (ha_) r.node = ca_;
+        else if (hb_) r.node = cb_;
+        else r.node = stack_pop(r, stack);
+    }
+#else
     {
         float4 n0, n1, n2, n3;
         load_node(sc.nodes, r.node, n0, n1, n2, n3);
@@ -325,6 +368,7 @@ __device__ __forceinline__ void lane_inner(const SceneDev& sc, LaneRay& r, int* 
         else if (hb) r.node = cb;
         else r.node = stack_pop(r, stack);
     }
+#endif
 }
 #if PT_BVH4
 // 4-wide visit (build variant, profiles/r02_c3_variants.md): four slab tests on one 128-byte node, the hits sorted by entry
