@@ -565,7 +565,11 @@ __global__ void k_lbvh_pack(int n, const uint32_t* __restrict__ sorted_ids, cons
     // (cx, cy) and (hx, hy) of a child sit in aligned pairs: the x and y slabs are evaluated by packed FFMA2 (pt_wavefront.cuh)
     nodes[4 * i + 0] = make_float4(ca.x, ca.y, ha.x, ha.y);
     nodes[4 * i + 1] = make_float4(cb.x, cb.y, hb.x, hb.y);
+#if PT_PACKED_SLABS == 2
+    nodes[4 * i + 2] = make_float4(ca.z, cb.z, ha.z, hb.z);     // z of both children as pairs too
+#else
     nodes[4 * i + 2] = make_float4(ca.z, ha.z, cb.z, hb.z);
+#endif
 #else
     nodes[4 * i + 0] = make_float4(ca.x, ca.y, ca.z, ha.x);
     nodes[4 * i + 1] = make_float4(ha.y, ha.z, cb.x, cb.y);
@@ -690,7 +694,11 @@ __global__ void k_lbvh_single(const int* __restrict__ bvh_prims, const float4* _
 #if PT_PACKED_SLABS
     nodes[0] = make_float4(c.x, c.y, h.x, h.y);
     nodes[1] = make_float4(0.f, 0.f, -1.f, -1.f);           // negative half-extent: near > far, never entered
+#if PT_PACKED_SLABS == 2
+    nodes[2] = make_float4(c.z, 0.f, h.z, -1.f);
+#else
     nodes[2] = make_float4(c.z, h.z, 0.f, -1.f);
+#endif
 #else
     nodes[0] = make_float4(c.x, c.y, c.z, h.x);
     nodes[1] = make_float4(h.y, h.z, 0.f, 0.f);

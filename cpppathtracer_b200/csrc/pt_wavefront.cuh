@@ -320,12 +320,24 @@ __device__ __forceinline__ void lane_inner(const SceneDev& sc, LaneRay& r, int* 
         float nax, nay, fax, fay, nbx, nby, fbx, fby;
         unpack2(fma2(ha, naxy, ta), nax, nay); unpack2(fma2(ha, axy, ta), fax, fay);
         unpack2(fma2(hb, naxy, tb), nbx, nby); unpack2(fma2(hb, axy, tb), fbx, fby);
-        const float taz = fmaf(caz, r.iz, -r.oz), tbz = fmaf(cbz, r.iz, -r.oz);
         const float lo = r.lo, hi = r.hi;
+#if PT_PACKED_SLABS == 2
+        // (caz, haz, cbz, hbz) hold (caz, cbz, haz, hbz): the z slabs of both children as one pair
+        const f32x2 czz = pack2(caz, haz), hzz = pack2(cbz, hbz), izz = pack2(r.iz, r.iz), nozz = pack2(-r.oz, -r.oz);
+        const f32x2 tzz = fma2(czz, izz, nozz);
+        float naz, nbz, faz, fbz;
+        unpack2(fma2(hzz, pack2(-az, -az), tzz), naz, nbz); unpack2(fma2(hzz, pack2(az, az), tzz), faz, fbz);
+        const float ea = fmaxf(fmaxf(nax, nay), fmaxf(naz, lo));
+        const float xa = fminf(fminf(fax, fay), fminf(faz, hi));
+        const float eb = fmaxf(fmaxf(nbx, nby), fmaxf(nbz, lo));
+        const float xb = fminf(fminf(fbx, fby), fminf(fbz, hi));
+#else
+        const float taz = fmaf(caz, r.iz, -r.oz), tbz = fmaf(cbz, r.iz, -r.oz);
         const float ea = fmaxf(fmaxf(nax, nay), fmaxf(fmaf(-haz, az, taz), lo));
         const float xa = fminf(fminf(fax, fay), fminf(fmaf(haz, az, taz), hi));
         const float eb = fmaxf(fmaxf(nbx, nby), fmaxf(fmaf(-hbz, az, tbz), lo));
         const float xb = fminf(fminf(fbx, fby), fminf(fmaf(hbz, az, tbz), hi));
+#endif
         const bool ha_ = ea <= xa, hb_ = eb <= xb;
         const int ca_ = __float_as_int(la), cb_ = __float_as_int(lb);
         if (ha_ && hb_) {
